@@ -1,0 +1,1019 @@
+// api.cu — the C ABI of include/mrsb.h: host bookkeeping around the kernels.
+// Every entry point cites the reference member it replaces in include/mrsb.h.
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "internal.h"
+#include "params.h"
+
+// ------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CU(call)                                                                                              \
+  do {                                                                                                        \
+    cudaError_t e_ = (call);                                                                                  \
+    if (e_ != cudaSuccess) return fail(MRSB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------
+// NCCL, loaded lazily so single-GPU users need no libnccl
+// ------------------------------------------------------------------------------------------
+struct NcclApi {
+  void* lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*)                                                         = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int)                                  = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t)                                                            = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t)    = nullptr;
+  ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)()                                                                       = nullptr;
+  ncclResult_t (*GroupEnd)()                                                                         = nullptr;
+  const char* (*GetErrorString)(ncclResult_t)                                                        = nullptr;
+};
+static NcclApi g_nccl;
+
+static int load_nccl() {
+  if (g_nccl.lib) return MRSB_OK;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  void*       lib     = nullptr;
+  for (const char* n : names) {
+    lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (lib) break;
+  }
+  if (!lib) return fail(MRSB_ERR_NCCL, "cannot dlopen libnccl.so.2: %s", dlerror());
+#define SYM(field, name)                                                          \
+  *(void**)(&g_nccl.field) = dlsym(lib, name);                                    \
+  if (!g_nccl.field) return fail(MRSB_ERR_NCCL, "libnccl lacks symbol %s", name);
+  SYM(GetUniqueId, "ncclGetUniqueId");
+  SYM(CommInitRank, "ncclCommInitRank");
+  SYM(CommDestroy, "ncclCommDestroy");
+  SYM(AllGather, "ncclAllGather");
+  SYM(Broadcast, "ncclBroadcast");
+  SYM(GroupStart, "ncclGroupStart");
+  SYM(GroupEnd, "ncclGroupEnd");
+  SYM(GetErrorString, "ncclGetErrorString");
+#undef SYM
+  g_nccl.lib = lib;
+  return MRSB_OK;
+}
+
+#define NC(call)                                                                                                  \
+  do {                                                                                                            \
+    ncclResult_t r_ = (call);                                                                                     \
+    if (r_ != ncclSuccess) return fail(MRSB_ERR_NCCL, "%s failed: %s", #call, g_nccl.GetErrorString(r_));          \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------
+// the handle
+// ------------------------------------------------------------------------------------------
+struct ParamSet {
+  mrsb_model_params      mp;
+  mrsb_controller_params cp;
+};
+
+struct mrsb_sim {
+  int          device = 0;
+  cudaStream_t stream = nullptr;
+  DevState     ds{};
+  DevGrid      grid{};
+
+  std::vector<ParamSet>      sets;
+  std::map<std::string, int> set_index;
+  std::vector<int32_t>       pset_host;  // [n_global]
+  DevParams*                 d_params     = nullptr;
+  int                        d_params_cap = 0;
+  int32_t*                   d_pset       = nullptr;
+  bool                       params_dirty = true;
+
+  char*    d_stage       = nullptr;  // staging for payload transposes
+  size_t   d_stage_bytes = 0;
+  int32_t* d_idx         = nullptr;
+  size_t   d_idx_cap     = 0;
+
+  int  uniform_mode = MRSB_INPUT_UNKNOWN;  // INPUT_MODE shared by all UAVs, or -1 if mixed
+  int  uniform_nm   = 0;                   // n_motors shared by all local UAVs, or 0 if mixed
+  bool any_moment   = false;
+
+  int    coll_enabled = 0, coll_crash = 0;
+  double coll_rebounce = 0.0;
+  void*  cub_tmp       = nullptr;
+  size_t cub_tmp_bytes = 0;
+
+  ncclComm_t           comm    = nullptr;
+  int                  n_ranks = 1, rank = 0;
+  std::vector<int64_t> shard_begin_of, shard_count_of;
+  bool                 equal_shards = true;
+
+  int64_t n_steps = 0, n_passes = 0, n_launches = 0;
+};
+
+static std::string set_key(const ParamSet& s) {
+  return std::string(reinterpret_cast<const char*>(&s), sizeof(ParamSet));
+}
+
+static int intern_set(mrsb_sim* h, const ParamSet& s) {
+  const std::string key = set_key(s);
+  auto              it  = h->set_index.find(key);
+  if (it != h->set_index.end()) return it->second;
+  const int id = int(h->sets.size());
+  h->sets.push_back(s);
+  h->set_index[key] = id;
+  h->params_dirty   = true;
+  return id;
+}
+
+static int check_params(const mrsb_model_params& p) {
+  if (p.n_motors < 1 || p.n_motors > MRSB_MAX_MOTORS) return fail(MRSB_ERR_INVALID, "n_motors=%d outside 1..%d", p.n_motors, MRSB_MAX_MOTORS);
+  return MRSB_OK;
+}
+
+static ParamSet canonical(const mrsb_model_params& mp, const mrsb_controller_params& cp) {
+  ParamSet s;
+  std::memset(&s, 0, sizeof(s));  // padding bytes take part in the key
+  s.mp.n_motors              = mp.n_motors;
+  s.mp.ground_enabled        = mp.ground_enabled != 0;
+  s.mp.takeoff_patch_enabled = mp.takeoff_patch_enabled != 0;
+  s.mp.g = mp.g, s.mp.mass = mp.mass, s.mp.kf = mp.kf, s.mp.km = mp.km, s.mp.prop_radius = mp.prop_radius, s.mp.arm_length = mp.arm_length;
+  s.mp.body_height = mp.body_height, s.mp.motor_time_constant = mp.motor_time_constant, s.mp.max_rpm = mp.max_rpm, s.mp.min_rpm = mp.min_rpm;
+  s.mp.air_resistance_coeff = mp.air_resistance_coeff, s.mp.ground_z = mp.ground_z;
+  std::memcpy(s.mp.J, mp.J, sizeof(mp.J));
+  for (int r = 0; r < 4; r++)
+    for (int m = 0; m < mp.n_motors; m++) s.mp.allocation_matrix[r * MRSB_MAX_MOTORS + m] = mp.allocation_matrix[r * MRSB_MAX_MOTORS + m];
+  s.cp.mixer_desaturation = cp.mixer_desaturation != 0;
+  s.cp.rate_kp = cp.rate_kp, s.cp.rate_kd = cp.rate_kd, s.cp.rate_ki = cp.rate_ki;
+  s.cp.att_kp = cp.att_kp, s.cp.att_kd = cp.att_kd, s.cp.att_ki = cp.att_ki, s.cp.att_max_rate_roll_pitch = cp.att_max_rate_roll_pitch,
+  s.cp.att_max_rate_yaw = cp.att_max_rate_yaw;
+  s.cp.vel_kp = cp.vel_kp, s.cp.vel_kd = cp.vel_kd, s.cp.vel_ki = cp.vel_ki, s.cp.vel_max_acceleration = cp.vel_max_acceleration;
+  s.cp.pos_kp = cp.pos_kp, s.cp.pos_kd = cp.pos_kd, s.cp.pos_ki = cp.pos_ki, s.cp.pos_max_velocity = cp.pos_max_velocity;
+  return s;
+}
+
+// upload the parameter table if it changed; recompute the launch specialisation hints
+static int flush_params(mrsb_sim* h) {
+  if (!h->params_dirty) return MRSB_OK;
+  const int n_sets = int(h->sets.size());
+  if (n_sets > h->d_params_cap) {
+    CU(cudaStreamSynchronize(h->stream));
+    if (h->d_params) CU(cudaFree(h->d_params));
+    h->d_params_cap = std::max(16, 2 * n_sets);
+    CU(cudaMalloc(&h->d_params, sizeof(DevParams) * h->d_params_cap));
+    h->ds.params = h->d_params;
+  }
+  std::vector<DevParams> host(n_sets);
+  for (int k = 0; k < n_sets; k++) mrsb_derive(h->sets[k].mp, h->sets[k].cp, &host[k]);
+  CU(cudaMemcpyAsync(h->d_params, host.data(), sizeof(DevParams) * n_sets, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));  // `host` goes out of scope
+  int nm = -1;
+  for (int64_t i = 0; i < h->ds.n; i++) {
+    const int m = h->sets[h->pset_host[h->ds.shard_begin + i]].mp.n_motors;
+    if (nm == -1) nm = m;
+    if (nm != m) {
+      nm = 0;
+      break;
+    }
+  }
+  h->uniform_nm   = nm > 0 ? nm : 0;
+  h->params_dirty = false;
+  return MRSB_OK;
+}
+
+static int ensure_stage(mrsb_sim* h, size_t bytes) {
+  if (bytes <= h->d_stage_bytes) return MRSB_OK;
+  CU(cudaStreamSynchronize(h->stream));
+  if (h->d_stage) CU(cudaFree(h->d_stage));
+  h->d_stage_bytes = std::max<size_t>(bytes, 1 << 16);
+  CU(cudaMalloc(&h->d_stage, h->d_stage_bytes));
+  return MRSB_OK;
+}
+
+// copy an index list to the device (nullptr stays nullptr = identity) after validating it
+static int stage_idx(mrsb_sim* h, int64_t n, const int32_t* idx, const int32_t** out) {
+  *out = nullptr;
+  if (n < 0 || n > h->ds.n && !idx) return fail(MRSB_ERR_INVALID, "n=%lld outside 0..%lld", (long long)n, (long long)h->ds.n);
+  if (!idx || n == 0) return MRSB_OK;
+  for (int64_t k = 0; k < n; k++)
+    if (idx[k] < 0 || idx[k] >= h->ds.n) return fail(MRSB_ERR_INVALID, "idx[%lld]=%d outside 0..%lld", (long long)k, idx[k], (long long)h->ds.n - 1);
+  if (size_t(n) > h->d_idx_cap) {
+    CU(cudaStreamSynchronize(h->stream));
+    if (h->d_idx) CU(cudaFree(h->d_idx));
+    h->d_idx_cap = std::max<size_t>(size_t(n), 1024);
+    CU(cudaMalloc(&h->d_idx, sizeof(int32_t) * h->d_idx_cap));
+  }
+  CU(cudaMemcpyAsync(h->d_idx, idx, sizeof(int32_t) * n, cudaMemcpyHostToDevice, h->stream));
+  *out = h->d_idx;
+  return MRSB_OK;
+}
+
+#define GUARD(h)                                              \
+  if (!(h)) return fail(MRSB_ERR_INVALID, "null handle");     \
+  CU(cudaSetDevice((h)->device));
+
+static int64_t round_up(int64_t v, int64_t m) {
+  return (v + m - 1) / m * m;
+}
+
+template <class T>
+static int dalloc(T** p, size_t count) {
+  CU(cudaMalloc(p, sizeof(T) * std::max<size_t>(count, 1)));
+  CU(cudaMemset(*p, 0, sizeof(T) * std::max<size_t>(count, 1)));
+  return MRSB_OK;
+}
+
+static int stride_of(int mode) {
+  switch (mode) {
+    case MRSB_ACTUATOR_CMD:
+      return MRSB_MAX_MOTORS;
+    case MRSB_ATTITUDE_CMD:
+      return 10;
+    case MRSB_TILT_HDG_RATE_CMD:
+      return 5;
+    default:
+      return 4;
+  }
+}
+
+// re-point the addressed UAVs to (possibly new) parameter sets produced by `edit`
+template <class Edit>
+static int repoint(mrsb_sim* h, int64_t n, const int32_t* idx, Edit edit) {
+  const int32_t* d_idx = nullptr;
+  int            rc    = stage_idx(h, n, idx, &d_idx);
+  if (rc) return rc;
+  if (n == 0) return MRSB_OK;
+  std::vector<int32_t> ids(static_cast<size_t>(n), 0);
+  std::map<int, int>   memo;
+  for (int64_t k = 0; k < n; k++) {
+    const int64_t i   = idx ? idx[k] : k;
+    const int     old = h->pset_host[size_t(h->ds.shard_begin + i)];
+    auto          it  = memo.find(old);
+    int           id;
+    if (it != memo.end()) {
+      id = it->second;
+    } else {
+      ParamSet s = h->sets[old];
+      edit(s);
+      id        = intern_set(h, canonical(s.mp, s.cp));
+      memo[old] = id;
+    }
+    ids[size_t(k)]                                 = id;
+    h->pset_host[size_t(h->ds.shard_begin + i)] = id;
+  }
+  h->params_dirty = true;
+  rc              = ensure_stage(h, sizeof(int32_t) * size_t(n));
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(h->d_stage, ids.data(), sizeof(int32_t) * size_t(n), cudaMemcpyHostToDevice, h->stream));
+  h->n_launches += launch_set_pset(h->d_pset, n, d_idx, h->ds.shard_begin, reinterpret_cast<const int32_t*>(h->d_stage), h->stream);
+  CU(cudaStreamSynchronize(h->stream));  // `ids` goes out of scope
+  return MRSB_OK;
+}
+
+extern "C" {
+
+const char* mrsb_last_error(void) {
+  return g_err;
+}
+int mrsb_version(void) {
+  return MRSB_VERSION_MAJOR * 1000 + MRSB_VERSION_MINOR;
+}
+
+// ------------------------------------------------------------------------------------------
+// lifetime
+// ------------------------------------------------------------------------------------------
+int mrsb_destroy(mrsb_handle h) {
+  if (!h) return MRSB_OK;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+  void* ptrs[] = {h->ds.st,     h->ds.vprev,  h->ds.rpm,      h->ds.pid,      h->ds.fext,         h->ds.mext,       h->ds.imu,    h->ds.initz,
+                  h->ds.cmd,    h->ds.ff,     h->ds.flags,    h->ds.mode,     h->ds.gpos,         h->d_params,      h->d_pset,    h->d_stage,
+                  h->d_idx,     h->grid.keys, h->grid.keys_sorted, h->grid.vals, h->grid.vals_sorted, h->grid.begin, h->grid.rec, h->grid.pairs,
+                  h->grid.counters, h->cub_tmp};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return MRSB_OK;
+}
+
+int mrsb_create(const mrsb_create_info* info, mrsb_handle* out) {
+  if (!info || !out) return fail(MRSB_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (info->n_types < 1 || !info->types) return fail(MRSB_ERR_INVALID, "need at least one airframe type");
+  if (info->n_local < 0 || info->n_global < info->n_local || info->shard_begin < 0 || info->shard_begin + info->n_local > info->n_global)
+    return fail(MRSB_ERR_INVALID, "inconsistent shard: n_local=%lld n_global=%lld shard_begin=%lld", (long long)info->n_local,
+                (long long)info->n_global, (long long)info->shard_begin);
+  if (info->n_global > 0x7fffffffLL) return fail(MRSB_ERR_INVALID, "n_global exceeds int32 indices");
+  for (int t = 0; t < info->n_types; t++) {
+    const int rc = check_params(info->types[t]);
+    if (rc) return rc;
+  }
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) return fail(MRSB_ERR_CUDA, "no CUDA device available (libmrsb has no CPU fallback)");
+  if (info->device < 0 || info->device >= n_dev) return fail(MRSB_ERR_INVALID, "device %d outside 0..%d", info->device, n_dev - 1);
+
+  mrsb_sim* h = new mrsb_sim();
+  h->device   = info->device;
+#define CREATE_CU(call)                      \
+  do {                                       \
+    int rc_ = [&]() -> int {                 \
+      CU(call);                              \
+      return MRSB_OK;                        \
+    }();                                     \
+    if (rc_) {                               \
+      mrsb_destroy(h);                       \
+      return rc_;                            \
+    }                                        \
+  } while (0)
+#define CREATE_RC(expr)  \
+  do {                   \
+    int rc_ = (expr);    \
+    if (rc_) {           \
+      mrsb_destroy(h);   \
+      return rc_;        \
+    }                    \
+  } while (0)
+
+  CREATE_CU(cudaSetDevice(h->device));
+  CREATE_CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+
+  DevState& s   = h->ds;
+  s.n           = info->n_local;
+  s.ld          = std::max<int64_t>(128, round_up(info->n_local, 128));
+  s.n_global    = info->n_global;
+  s.shard_begin = info->shard_begin;
+  const size_t ld = size_t(s.ld);
+  CREATE_RC(dalloc(&s.st, 18 * ld));
+  CREATE_RC(dalloc(&s.vprev, 3 * ld));
+  CREATE_RC(dalloc(&s.rpm, MRSB_NM * ld));
+  CREATE_RC(dalloc(&s.pid, PID_ROWS * ld));
+  CREATE_RC(dalloc(&s.fext, 3 * ld));
+  CREATE_RC(dalloc(&s.mext, 3 * ld));
+  CREATE_RC(dalloc(&s.imu, 3 * ld));
+  CREATE_RC(dalloc(&s.initz, ld));
+  CREATE_RC(dalloc(&s.cmd, CMD_ROWS * ld));
+  CREATE_RC(dalloc(&s.ff, FF_ROWS * ld));
+  CREATE_RC(dalloc(&s.flags, ld));
+  CREATE_RC(dalloc(&s.mode, ld));
+  CREATE_RC(dalloc(&s.gpos, 3 * size_t(s.n_global)));
+  CREATE_RC(dalloc(&h->d_pset, size_t(s.n_global)));
+  s.pset = h->d_pset;
+
+  // parameter sets: one per airframe type with default controller gains (US:159-169)
+  mrsb_controller_params cp;
+  mrsb_controller_params_default(&cp);
+  std::vector<int> set_of_type(info->n_types);
+  for (int t = 0; t < info->n_types; t++) set_of_type[t] = intern_set(h, canonical(info->types[t], cp));
+  h->pset_host.resize(size_t(s.n_global));
+  for (int64_t j = 0; j < s.n_global; j++) {
+    const int t = info->type_of_uav ? info->type_of_uav[j] : 0;
+    if (t < 0 || t >= info->n_types) {
+      mrsb_destroy(h);
+      return fail(MRSB_ERR_INVALID, "type_of_uav[%lld]=%d outside 0..%d", (long long)j, t, info->n_types - 1);
+    }
+    h->pset_host[size_t(j)] = set_of_type[t];
+  }
+  CREATE_CU(cudaMemcpy(h->d_pset, h->pset_host.data(), sizeof(int32_t) * size_t(s.n_global), cudaMemcpyHostToDevice));
+  CREATE_RC(flush_params(h));
+
+  // initial state (MM:183-198 + setStatePos MM:439-446): R = Rz(-heading), flags from the airframe
+  {
+    std::vector<uint32_t> fl(ld, 0u);
+    for (int64_t i = 0; i < s.n; i++)
+      fl[size_t(i)] = h->sets[h->pset_host[size_t(s.shard_begin + i)]].mp.takeoff_patch_enabled ? FLAG_TAKEOFF : 0u;
+    CREATE_CU(cudaMemcpy(s.flags, fl.data(), sizeof(uint32_t) * ld, cudaMemcpyHostToDevice));
+    const size_t bytes = sizeof(double) * 4 * size_t(std::max<int64_t>(s.n, 1));
+    CREATE_RC(ensure_stage(h, bytes));
+    double* d_xyz = nullptr;
+    double* d_hdg = nullptr;
+    if (info->spawn_xyz && s.n) {
+      d_xyz = reinterpret_cast<double*>(h->d_stage);
+      CREATE_CU(cudaMemcpyAsync(d_xyz, info->spawn_xyz, sizeof(double) * 3 * s.n, cudaMemcpyHostToDevice, h->stream));
+    }
+    if (info->spawn_heading && s.n) {
+      d_hdg = reinterpret_cast<double*>(h->d_stage) + 3 * s.n;
+      CREATE_CU(cudaMemcpyAsync(d_hdg, info->spawn_heading, sizeof(double) * s.n, cudaMemcpyHostToDevice, h->stream));
+    }
+    h->n_launches += launch_set_state_pos(s, s.n, nullptr, d_xyz, d_hdg, h->stream);
+    CREATE_CU(cudaStreamSynchronize(h->stream));
+  }
+
+  // collision workspace
+  {
+    DevGrid&     g  = h->grid;
+    const size_t ng = size_t(std::max<int64_t>(s.n_global, 1));
+    uint32_t     bits = 10;
+    while ((size_t(1) << bits) < 2 * ng && bits < 30) bits++;
+    g.bits      = bits;
+    g.n_buckets = 1u << bits;
+    CREATE_RC(dalloc(&g.keys, ng));
+    CREATE_RC(dalloc(&g.keys_sorted, ng));
+    CREATE_RC(dalloc(&g.vals, ng));
+    CREATE_RC(dalloc(&g.vals_sorted, ng));
+    CREATE_RC(dalloc(&g.begin, size_t(g.n_buckets) + 1));
+    CREATE_RC(dalloc(&g.rec, ng));
+    g.pair_cap = int64_t(std::max<size_t>(4096, 4 * size_t(std::max<int64_t>(s.n, 1))));
+    CREATE_RC(dalloc(&g.pairs, 2 * size_t(g.pair_cap)));
+    CREATE_RC(dalloc(&g.counters, 4));
+    h->cub_tmp_bytes = collide_tmp_bytes(s.n_global);
+    CREATE_CU(cudaMalloc(&h->cub_tmp, std::max<size_t>(h->cub_tmp_bytes, 16)));
+  }
+  h->shard_begin_of = {s.shard_begin};
+  h->shard_count_of = {s.n};
+  CREATE_CU(cudaStreamSynchronize(h->stream));
+  *out = h;
+  return MRSB_OK;
+}
+
+int mrsb_sync(mrsb_handle h) {
+  GUARD(h);
+  CU(cudaStreamSynchronize(h->stream));
+  return MRSB_OK;
+}
+int64_t mrsb_n_local(mrsb_handle h) {
+  return h ? h->ds.n : -1;
+}
+int64_t mrsb_n_global(mrsb_handle h) {
+  return h ? h->ds.n_global : -1;
+}
+void* mrsb_get_stream(mrsb_handle h) {
+  return h ? (void*)h->stream : nullptr;
+}
+
+// ------------------------------------------------------------------------------------------
+// commands
+// ------------------------------------------------------------------------------------------
+static void note_mode(mrsb_sim* h, int mode, int64_t n, bool all) {
+  if (all && n == h->ds.n) {
+    h->uniform_mode = mode;
+  } else if (n > 0 && h->uniform_mode != mode) {
+    h->uniform_mode = -1;
+  }
+}
+
+int mrsb_set_input_device(mrsb_handle h, int32_t mode, int64_t n, const int32_t* idx_dev, const double* payload_dev, int32_t stride) {
+  GUARD(h);
+  if (mode < MRSB_INPUT_UNKNOWN || mode > MRSB_POSITION_CMD) return fail(MRSB_ERR_INVALID, "mode %d is not an INPUT_MODE", mode);
+  if (n < 0 || (!idx_dev && n > h->ds.n)) return fail(MRSB_ERR_INVALID, "n=%lld outside 0..%lld", (long long)n, (long long)h->ds.n);
+  if (mode == MRSB_INPUT_UNKNOWN) {
+    h->n_launches += launch_set_mode(h->ds, n, idx_dev, mode, h->stream);
+  } else {
+    if (!payload_dev) return fail(MRSB_ERR_INVALID, "null payload");
+    if (stride < (mode == MRSB_ACTUATOR_CMD ? 1 : stride_of(mode))) return fail(MRSB_ERR_INVALID, "stride %d too small for mode %d", stride, mode);
+    h->n_launches += launch_scatter_input(h->ds, mode, n, idx_dev, payload_dev, stride, h->stream);
+  }
+  note_mode(h, mode, n, idx_dev == nullptr);
+  CU(cudaGetLastError());
+  return MRSB_OK;
+}
+
+int mrsb_set_input(mrsb_handle h, int32_t mode, int64_t n, const int32_t* idx, const double* payload, int32_t stride) {
+  GUARD(h);
+  if (mode < MRSB_INPUT_UNKNOWN || mode > MRSB_POSITION_CMD) return fail(MRSB_ERR_INVALID, "mode %d is not an INPUT_MODE", mode);
+  const int32_t* d_idx = nullptr;
+  int            rc    = stage_idx(h, n, idx, &d_idx);
+  if (rc) return rc;
+  if (mode == MRSB_INPUT_UNKNOWN) {
+    h->n_launches += launch_set_mode(h->ds, n, d_idx, mode, h->stream);
+    note_mode(h, mode, n, idx == nullptr);
+    return MRSB_OK;
+  }
+  if (!payload && n) return fail(MRSB_ERR_INVALID, "null payload");
+  if (stride < (mode == MRSB_ACTUATOR_CMD ? 1 : stride_of(mode))) return fail(MRSB_ERR_INVALID, "stride %d too small for mode %d", stride, mode);
+  if (n == 0) return MRSB_OK;
+  const size_t bytes = sizeof(double) * size_t(n) * size_t(stride);
+  rc                 = ensure_stage(h, bytes);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(h->d_stage, payload, bytes, cudaMemcpyHostToDevice, h->stream));
+  h->n_launches += launch_scatter_input(h->ds, mode, n, d_idx, reinterpret_cast<const double*>(h->d_stage), stride, h->stream);
+  note_mode(h, mode, n, idx == nullptr);
+  CU(cudaGetLastError());
+  return MRSB_OK;
+}
+
+#define SET_INPUT(name, MODE, STRIDE)                                                                        \
+  int mrsb_set_input_##name(mrsb_handle h, int64_t n, const int32_t* idx, const double* payload) {           \
+    return mrsb_set_input(h, MODE, n, idx, payload, STRIDE);                                                 \
+  }
+SET_INPUT(actuators, MRSB_ACTUATOR_CMD, MRSB_MAX_MOTORS)
+SET_INPUT(control_group, MRSB_CONTROL_GROUP_CMD, 4)
+SET_INPUT(attitude_rate, MRSB_ATTITUDE_RATE_CMD, 4)
+SET_INPUT(attitude, MRSB_ATTITUDE_CMD, 10)
+SET_INPUT(tilt_hdg_rate, MRSB_TILT_HDG_RATE_CMD, 5)
+SET_INPUT(acceleration_hdg_rate, MRSB_ACCELERATION_HDG_RATE_CMD, 4)
+SET_INPUT(acceleration_hdg, MRSB_ACCELERATION_HDG_CMD, 4)
+SET_INPUT(velocity_hdg_rate, MRSB_VELOCITY_HDG_RATE_CMD, 4)
+SET_INPUT(velocity_hdg, MRSB_VELOCITY_HDG_CMD, 4)
+SET_INPUT(position, MRSB_POSITION_CMD, 4)
+#undef SET_INPUT
+
+int mrsb_clear_input(mrsb_handle h, int64_t n, const int32_t* idx) {
+  return mrsb_set_input(h, MRSB_INPUT_UNKNOWN, n, idx, nullptr, 0);
+}
+
+// host rows -> SoA rows [row0, row0+rows) of `dst`; then OR `flag` into the per-UAV flags
+static int put_rows(mrsb_sim* h, double* dst, int rows, int64_t n, const int32_t* idx, const double* payload, int stride, uint32_t or_flag) {
+  const int32_t* d_idx = nullptr;
+  int            rc    = stage_idx(h, n, idx, &d_idx);
+  if (rc) return rc;
+  if (n == 0) return MRSB_OK;
+  if (!payload) return fail(MRSB_ERR_INVALID, "null payload");
+  const size_t bytes = sizeof(double) * size_t(n) * size_t(stride);
+  rc                 = ensure_stage(h, bytes);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(h->d_stage, payload, bytes, cudaMemcpyHostToDevice, h->stream));
+  h->n_launches += launch_scatter_rows(dst, h->ds.ld, rows, n, d_idx, reinterpret_cast<const double*>(h->d_stage), stride, 0, h->stream);
+  if (or_flag) h->n_launches += launch_flag_update(h->ds, n, d_idx, 0xffffffffu, or_flag, h->stream);
+  CU(cudaGetLastError());
+  return MRSB_OK;
+}
+
+static int get_rows(mrsb_sim* h, const double* src, int rows, int64_t n, const int32_t* idx, double* out) {
+  const int32_t* d_idx = nullptr;
+  int            rc    = stage_idx(h, n, idx, &d_idx);
+  if (rc) return rc;
+  if (n == 0) return MRSB_OK;
+  const size_t bytes = sizeof(double) * size_t(n) * size_t(rows);
+  rc                 = ensure_stage(h, bytes);
+  if (rc) return rc;
+  h->n_launches += launch_gather_rows(src, h->ds.ld, rows, n, d_idx, reinterpret_cast<double*>(h->d_stage), rows, 0, h->stream);
+  CU(cudaMemcpyAsync(out, h->d_stage, bytes, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return MRSB_OK;
+}
+
+int mrsb_set_feedforward_acceleration_hdg_rate(mrsb_handle h, int64_t n, const int32_t* idx, const double* payload) {
+  GUARD(h);
+  return put_rows(h, h->ds.ff + FF_ACC_HDG_RATE * h->ds.ld, 4, n, idx, payload, 4, FLAG_FF_ACC_HDG_RATE);
+}
+int mrsb_set_feedforward_acceleration_hdg(mrsb_handle h, int64_t n, const int32_t* idx, const double* payload) {
+  GUARD(h);
+  return put_rows(h, h->ds.ff + FF_ACC_HDG * h->ds.ld, 3, n, idx, payload, 4, FLAG_FF_ACC_HDG);
+}
+int mrsb_set_feedforward_velocity_hdg(mrsb_handle h, int64_t n, const int32_t* idx, const double* payload) {
+  GUARD(h);
+  return put_rows(h, h->ds.ff + FF_VEL_HDG * h->ds.ld, 3, n, idx, payload, 4, FLAG_FF_VEL_HDG);
+}
+int mrsb_set_feedforward_velocity_hdg_rate(mrsb_handle h, int64_t n, const int32_t* idx, const double* payload) {
+  GUARD(h);
+  return put_rows(h, h->ds.ff + FF_VEL_HDG_RATE * h->ds.ld, 3, n, idx, payload, 4, FLAG_FF_VEL_HDG_RATE);
+}
+int mrsb_clear_feedforward(mrsb_handle h, int64_t n, const int32_t* idx) {
+  GUARD(h);
+  const int32_t* d_idx = nullptr;
+  int            rc    = stage_idx(h, n, idx, &d_idx);
+  if (rc) return rc;
+  h->n_launches += launch_flag_update(h->ds, n, d_idx, ~(FLAG_FF_ACC_HDG | FLAG_FF_ACC_HDG_RATE | FLAG_FF_VEL_HDG | FLAG_FF_VEL_HDG_RATE), 0u, h->stream);
+  return MRSB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// stepping
+// ------------------------------------------------------------------------------------------
+static int exchange_positions(mrsb_sim* h) {
+  if (h->n_ranks <= 1) return MRSB_OK;
+  if (!h->comm) return fail(MRSB_ERR_STATE, "sharded handle (n_global > n_local) without a communicator: call mrsb_comm_init_nccl, or use mrsb_gather_buffer + mrsb_handle_collisions_gathered");
+  double* buf = h->ds.gpos;
+  if (h->equal_shards) {
+    NC(g_nccl.AllGather(buf + 3 * h->ds.shard_begin, buf, size_t(3 * h->ds.n), ncclDouble, h->comm, h->stream));
+  } else {
+    NC(g_nccl.GroupStart());
+    for (int r = 0; r < h->n_ranks; r++) {
+      double* p = buf + 3 * h->shard_begin_of[r];
+      NC(g_nccl.Broadcast(p, p, size_t(3 * h->shard_count_of[r]), ncclDouble, r, h->comm, h->stream));
+    }
+    NC(g_nccl.GroupEnd());
+  }
+  return MRSB_OK;
+}
+
+static int collide_local(mrsb_sim* h) {
+  h->n_launches += launch_collide(h->ds, h->grid, h->coll_crash, h->coll_rebounce, h->cub_tmp, h->cub_tmp_bytes, h->stream);
+  h->n_passes++;
+  CU(cudaGetLastError());
+  return MRSB_OK;
+}
+
+int mrsb_make_step(mrsb_handle h, double dt, int32_t k_substeps) {
+  GUARD(h);
+  if (k_substeps < 1) return fail(MRSB_ERR_INVALID, "k_substeps must be >= 1");
+  int rc = flush_params(h);
+  if (rc) return rc;
+  h->n_launches += launch_step(h->ds, dt, k_substeps, h->uniform_mode, h->uniform_nm, h->any_moment, h->stream);
+  h->n_steps += k_substeps;
+  CU(cudaGetLastError());
+  return MRSB_OK;
+}
+
+int mrsb_handle_collisions(mrsb_handle h) {
+  GUARD(h);
+  if (!(h->coll_crash || h->coll_enabled)) return MRSB_OK;  // SIM:299-301
+  int rc = flush_params(h);
+  if (rc) return rc;
+  if (h->ds.n_global > h->ds.n && h->n_ranks <= 1) return fail(MRSB_ERR_STATE, "sharded handle without communicator");
+  rc = exchange_positions(h);
+  if (rc) return rc;
+  return collide_local(h);
+}
+
+int mrsb_handle_collisions_gathered(mrsb_handle h) {
+  GUARD(h);
+  if (!(h->coll_crash || h->coll_enabled)) return MRSB_OK;
+  int rc = flush_params(h);
+  if (rc) return rc;
+  return collide_local(h);
+}
+
+int mrsb_run(mrsb_handle h, double dt, int32_t k_substeps, int32_t n_ticks, int32_t with_collisions) {
+  GUARD(h);
+  for (int t = 0; t < n_ticks; t++) {
+    int rc = mrsb_make_step(h, dt, k_substeps);
+    if (rc) return rc;
+    if (with_collisions) {
+      rc = mrsb_handle_collisions(h);
+      if (rc) return rc;
+    }
+  }
+  return MRSB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// state access
+// ------------------------------------------------------------------------------------------
+int mrsb_get_state(mrsb_handle h, int64_t n, const int32_t* idx, double* x, double* v, double* R, double* omega, double* motor_rpm) {
+  GUARD(h);
+  const int64_t ld = h->ds.ld;
+  int           rc = MRSB_OK;
+  if (x && !rc) rc = get_rows(h, h->ds.st + 0 * ld, 3, n, idx, x);
+  if (v && !rc) rc = get_rows(h, h->ds.st + 3 * ld, 3, n, idx, v);
+  if (R && !rc) rc = get_rows(h, h->ds.st + 6 * ld, 9, n, idx, R);
+  if (omega && !rc) rc = get_rows(h, h->ds.st + 15 * ld, 3, n, idx, omega);
+  if (motor_rpm && !rc) rc = get_rows(h, h->ds.rpm, MRSB_NM, n, idx, motor_rpm);
+  return rc;
+}
+
+int mrsb_get_v_prev(mrsb_handle h, int64_t n, const int32_t* idx, double* v_prev) {
+  GUARD(h);
+  const int32_t* d_idx = nullptr;
+  int            rc    = stage_idx(h, n, idx, &d_idx);
+  if (rc) return rc;
+  if (n == 0) return MRSB_OK;
+  rc = ensure_stage(h, sizeof(double) * 3 * size_t(n));
+  if (rc) return rc;
+  h->n_launches += launch_gather_vprev(h->ds, n, d_idx, reinterpret_cast<double*>(h->d_stage), h->stream);
+  CU(cudaMemcpyAsync(v_prev, h->d_stage, sizeof(double) * 3 * size_t(n), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return MRSB_OK;
+}
+
+int mrsb_get_imu_acceleration(mrsb_handle h, int64_t n, const int32_t* idx, double* acc) {
+  GUARD(h);
+  return get_rows(h, h->ds.imu, 3, n, idx, acc);
+}
+
+int mrsb_set_state(mrsb_handle h, int64_t n, const int32_t* idx, const double* x, const double* v, const double* R, const double* omega,
+                   const double* motor_rpm) {
+  GUARD(h);
+  const int64_t ld = h->ds.ld;
+  int           rc = MRSB_OK;
+  if (v) {
+    const int32_t* d_idx = nullptr;
+    rc                   = stage_idx(h, n, idx, &d_idx);
+    if (rc) return rc;
+    h->n_launches += launch_stash_vprev(h->ds, n, d_idx, h->stream);
+  }
+  if (x && !rc) rc = put_rows(h, h->ds.st + 0 * ld, 3, n, idx, x, 3, 0);
+  if (v && !rc) rc = put_rows(h, h->ds.st + 3 * ld, 3, n, idx, v, 3, 0);
+  if (R && !rc) rc = put_rows(h, h->ds.st + 6 * ld, 9, n, idx, R, 9, 0);
+  if (omega && !rc) rc = put_rows(h, h->ds.st + 15 * ld, 3, n, idx, omega, 3, 0);
+  if (motor_rpm && !rc) rc = put_rows(h, h->ds.rpm, MRSB_NM, n, idx, motor_rpm, MRSB_NM, 0);
+  if (x && !rc) h->n_launches += launch_publish_positions(h->ds, h->stream);
+  return rc;
+}
+
+int mrsb_set_state_pos(mrsb_handle h, int64_t n, const int32_t* idx, const double* xyz, const double* heading) {
+  GUARD(h);
+  const int32_t* d_idx = nullptr;
+  int            rc    = stage_idx(h, n, idx, &d_idx);
+  if (rc) return rc;
+  if (n == 0) return MRSB_OK;
+  if (!xyz || !heading) return fail(MRSB_ERR_INVALID, "null payload");
+  rc = ensure_stage(h, sizeof(double) * 4 * size_t(n));
+  if (rc) return rc;
+  double* d_xyz = reinterpret_cast<double*>(h->d_stage);
+  double* d_hdg = d_xyz + 3 * n;
+  CU(cudaMemcpyAsync(d_xyz, xyz, sizeof(double) * 3 * size_t(n), cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(d_hdg, heading, sizeof(double) * size_t(n), cudaMemcpyHostToDevice, h->stream));
+  h->n_launches += launch_set_state_pos(h->ds, n, d_idx, d_xyz, d_hdg, h->stream);
+  CU(cudaGetLastError());
+  return MRSB_OK;
+}
+
+int mrsb_get_input_mode(mrsb_handle h, int64_t n, const int32_t* idx, int32_t* mode) {
+  GUARD(h);
+  const int32_t* d_idx = nullptr;
+  int            rc    = stage_idx(h, n, idx, &d_idx);
+  if (rc) return rc;
+  if (n == 0) return MRSB_OK;
+  rc = ensure_stage(h, sizeof(int32_t) * size_t(n));
+  if (rc) return rc;
+  h->n_launches += launch_gather_u8(h->ds.mode, n, d_idx, reinterpret_cast<int32_t*>(h->d_stage), h->stream);
+  CU(cudaMemcpyAsync(mode, h->d_stage, sizeof(int32_t) * size_t(n), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return MRSB_OK;
+}
+
+static int get_flags(mrsb_sim* h, int64_t n, const int32_t* idx, std::vector<uint32_t>& out) {
+  const int32_t* d_idx = nullptr;
+  int            rc    = stage_idx(h, n, idx, &d_idx);
+  if (rc) return rc;
+  out.resize(size_t(n));
+  if (n == 0) return MRSB_OK;
+  rc = ensure_stage(h, sizeof(uint32_t) * size_t(n));
+  if (rc) return rc;
+  h->n_launches += launch_gather_u32(h->ds.flags, n, d_idx, reinterpret_cast<uint32_t*>(h->d_stage), h->stream);
+  CU(cudaMemcpyAsync(out.data(), h->d_stage, sizeof(uint32_t) * size_t(n), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return MRSB_OK;
+}
+
+int mrsb_crash(mrsb_handle h, int64_t n, const int32_t* idx) {
+  GUARD(h);
+  const int32_t* d_idx = nullptr;
+  int            rc    = stage_idx(h, n, idx, &d_idx);
+  if (rc) return rc;
+  h->n_launches += launch_flag_update(h->ds, n, d_idx, 0xffffffffu, FLAG_CRASHED, h->stream);
+  return MRSB_OK;
+}
+
+int mrsb_has_crashed(mrsb_handle h, int64_t n, const int32_t* idx, int32_t* crashed) {
+  GUARD(h);
+  std::vector<uint32_t> fl;
+  int                   rc = get_flags(h, n, idx, fl);
+  if (rc) return rc;
+  for (int64_t k = 0; k < n; k++) crashed[k] = (fl[size_t(k)] & FLAG_CRASHED) ? 1 : 0;
+  return MRSB_OK;
+}
+
+int mrsb_apply_force(mrsb_handle h, int64_t n, const int32_t* idx, const double* force) {
+  GUARD(h);
+  return put_rows(h, h->ds.fext, 3, n, idx, force, 3, 0);
+}
+int mrsb_get_external_force(mrsb_handle h, int64_t n, const int32_t* idx, double* force) {
+  GUARD(h);
+  return get_rows(h, h->ds.fext, 3, n, idx, force);
+}
+int mrsb_set_external_moment(mrsb_handle h, int64_t n, const int32_t* idx, const double* moment) {
+  GUARD(h);
+  h->any_moment = true;
+  return put_rows(h, h->ds.mext, 3, n, idx, moment, 3, 0);
+}
+
+// ------------------------------------------------------------------------------------------
+// parameters
+// ------------------------------------------------------------------------------------------
+static int check_uav(mrsb_sim* h, int64_t uav) {
+  if (uav < 0 || uav >= h->ds.n) return fail(MRSB_ERR_INVALID, "uav %lld outside 0..%lld", (long long)uav, (long long)h->ds.n - 1);
+  return MRSB_OK;
+}
+
+int mrsb_get_params(mrsb_handle h, int64_t uav, mrsb_model_params* out) {
+  GUARD(h);
+  int rc = check_uav(h, uav);
+  if (rc) return rc;
+  *out = h->sets[h->pset_host[size_t(h->ds.shard_begin + uav)]].mp;
+  std::vector<uint32_t> fl;
+  const int32_t         one = int32_t(uav);
+  rc                        = get_flags(h, 1, &one, fl);
+  if (rc) return rc;
+  out->takeoff_patch_enabled = (fl[0] & FLAG_TAKEOFF) ? 1 : 0;
+  return MRSB_OK;
+}
+
+int mrsb_get_controller_params(mrsb_handle h, int64_t uav, mrsb_controller_params* out) {
+  GUARD(h);
+  int rc = check_uav(h, uav);
+  if (rc) return rc;
+  *out = h->sets[h->pset_host[size_t(h->ds.shard_begin + uav)]].cp;
+  return MRSB_OK;
+}
+
+int mrsb_get_mixer_allocation(mrsb_handle h, int64_t uav, double* out) {
+  GUARD(h);
+  int rc = check_uav(h, uav);
+  if (rc) return rc;
+  double mix[MRSB_MAX_MOTORS][4];
+  mrsb_mixer_allocation(h->sets[h->pset_host[size_t(h->ds.shard_begin + uav)]].mp, mix);
+  std::memcpy(out, mix, sizeof(mix));
+  return MRSB_OK;
+}
+
+int mrsb_set_params(mrsb_handle h, int64_t n, const int32_t* idx, const mrsb_model_params* params) {
+  GUARD(h);
+  if (!params) return fail(MRSB_ERR_INVALID, "null params");
+  int rc = check_params(*params);
+  if (rc) return rc;
+  mrsb_controller_params def;
+  mrsb_controller_params_default(&def);
+  rc = repoint(h, n, idx, [&](ParamSet& s) {  // US:404-409: new model params, controllers re-created with default gains
+    s.mp = *params;
+    s.cp = def;
+  });
+  if (rc) return rc;
+  const int32_t* d_idx = nullptr;
+  rc                   = stage_idx(h, n, idx, &d_idx);
+  if (rc) return rc;
+  h->n_launches += launch_reset_pid(h->ds, n, d_idx, 0, PID_ROWS, h->stream);
+  h->n_launches += launch_flag_update(h->ds, n, d_idx, ~FLAG_TAKEOFF, params->takeoff_patch_enabled ? FLAG_TAKEOFF : 0u, h->stream);
+  return MRSB_OK;
+}
+
+static int set_ctrl(mrsb_sim* h, int64_t n, const int32_t* idx, int pid_row0, int pid_rows, void (*edit)(ParamSet&, const double*), const double* v) {
+  int rc = repoint(h, n, idx, [&](ParamSet& s) { edit(s, v); });
+  if (rc) return rc;
+  if (pid_rows) {
+    const int32_t* d_idx = nullptr;
+    rc                   = stage_idx(h, n, idx, &d_idx);
+    if (rc) return rc;
+    h->n_launches += launch_reset_pid(h->ds, n, d_idx, pid_row0, pid_rows, h->stream);
+  }
+  return MRSB_OK;
+}
+
+int mrsb_set_mixer_params(mrsb_handle h, int64_t n, const int32_t* idx, int32_t desaturation) {
+  GUARD(h);
+  const double v[1] = {double(desaturation)};
+  return set_ctrl(h, n, idx, 0, 0, [](ParamSet& s, const double* v) { s.cp.mixer_desaturation = v[0] != 0.0; }, v);
+}
+int mrsb_set_rate_controller_params(mrsb_handle h, int64_t n, const int32_t* idx, double kp, double kd, double ki) {
+  GUARD(h);
+  const double v[3] = {kp, kd, ki};
+  return set_ctrl(h, n, idx, 18, 6, [](ParamSet& s, const double* v) { s.cp.rate_kp = v[0], s.cp.rate_kd = v[1], s.cp.rate_ki = v[2]; }, v);
+}
+int mrsb_set_attitude_controller_params(mrsb_handle h, int64_t n, const int32_t* idx, double kp, double kd, double ki, double max_rate_roll_pitch,
+                                        double max_rate_yaw) {
+  GUARD(h);
+  const double v[5] = {kp, kd, ki, max_rate_roll_pitch, max_rate_yaw};
+  return set_ctrl(h, n, idx, 12, 6, [](ParamSet& s, const double* v) {
+    s.cp.att_kp = v[0], s.cp.att_kd = v[1], s.cp.att_ki = v[2], s.cp.att_max_rate_roll_pitch = v[3], s.cp.att_max_rate_yaw = v[4];
+  }, v);
+}
+int mrsb_set_velocity_controller_params(mrsb_handle h, int64_t n, const int32_t* idx, double kp, double kd, double ki, double max_acceleration) {
+  GUARD(h);
+  const double v[4] = {kp, kd, ki, max_acceleration};
+  return set_ctrl(h, n, idx, 6, 6, [](ParamSet& s, const double* v) {
+    s.cp.vel_kp = v[0], s.cp.vel_kd = v[1], s.cp.vel_ki = v[2], s.cp.vel_max_acceleration = v[3];
+  }, v);
+}
+int mrsb_set_position_controller_params(mrsb_handle h, int64_t n, const int32_t* idx, double kp, double kd, double ki, double max_velocity) {
+  GUARD(h);
+  const double v[4] = {kp, kd, ki, max_velocity};
+  return set_ctrl(h, n, idx, 0, 6, [](ParamSet& s, const double* v) {
+    s.cp.pos_kp = v[0], s.cp.pos_kd = v[1], s.cp.pos_ki = v[2], s.cp.pos_max_velocity = v[3];
+  }, v);
+}
+
+// ------------------------------------------------------------------------------------------
+// collisions
+// ------------------------------------------------------------------------------------------
+int mrsb_set_collisions(mrsb_handle h, int32_t enabled, int32_t crash, double rebounce) {
+  GUARD(h);
+  h->coll_enabled  = enabled != 0;
+  h->coll_crash    = crash != 0;
+  h->coll_rebounce = rebounce;
+  return MRSB_OK;
+}
+
+int mrsb_get_collision_pairs(mrsb_handle h, int32_t* ij, int64_t cap, int64_t* count) {
+  GUARD(h);
+  unsigned long long found = 0;
+  CU(cudaMemcpyAsync(&found, h->grid.counters, sizeof(found), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  if (count) *count = int64_t(found);
+  if (int64_t(found) > h->grid.pair_cap)
+    return fail(MRSB_ERR_CAPACITY, "%llu pairs found but the device pair buffer holds %lld", found, (long long)h->grid.pair_cap);
+  if (!ij || found == 0) return MRSB_OK;
+  std::vector<int32_t> tmp(2 * size_t(found));
+  CU(cudaMemcpy(tmp.data(), h->grid.pairs, sizeof(int32_t) * tmp.size(), cudaMemcpyDeviceToHost));
+  std::vector<std::pair<int32_t, int32_t>> pr(static_cast<size_t>(found), std::pair<int32_t, int32_t>(0, 0));
+  for (size_t k = 0; k < pr.size(); k++) pr[k] = {tmp[2 * k], tmp[2 * k + 1]};
+  std::sort(pr.begin(), pr.end());
+  const int64_t m = std::min<int64_t>(cap, int64_t(found));
+  for (int64_t k = 0; k < m; k++) {
+    ij[2 * k]     = pr[size_t(k)].first;
+    ij[2 * k + 1] = pr[size_t(k)].second;
+  }
+  if (int64_t(found) > cap) return fail(MRSB_ERR_CAPACITY, "%llu pairs found, caller buffer holds %lld", found, (long long)cap);
+  return MRSB_OK;
+}
+
+int mrsb_get_counters(mrsb_handle h, int64_t* out5) {
+  GUARD(h);
+  unsigned long long found = 0;
+  CU(cudaMemcpyAsync(&found, h->grid.counters, sizeof(found), cudaMemcpyDeviceToHost, h->stream));
+  std::vector<uint32_t> fl;
+  int                   rc = get_flags(h, h->ds.n, nullptr, fl);
+  if (rc) return rc;
+  int64_t crashed = 0;
+  for (uint32_t f : fl) crashed += (f & FLAG_CRASHED) ? 1 : 0;
+  out5[0] = h->n_steps;
+  out5[1] = h->n_passes;
+  out5[2] = int64_t(found);
+  out5[3] = crashed;
+  out5[4] = h->n_launches;
+  return MRSB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// sharded operation
+// ------------------------------------------------------------------------------------------
+int mrsb_nccl_unique_id(void* out128) {
+  int rc = load_nccl();
+  if (rc) return rc;
+  ncclUniqueId id;
+  NC(g_nccl.GetUniqueId(&id));
+  std::memcpy(out128, &id, sizeof(id));
+  return MRSB_OK;
+}
+
+int mrsb_comm_init_nccl(mrsb_handle h, int32_t n_ranks, int32_t rank, const void* unique_id128) {
+  GUARD(h);
+  int rc = load_nccl();
+  if (rc) return rc;
+  if (n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(MRSB_ERR_INVALID, "bad rank %d of %d", rank, n_ranks);
+  ncclUniqueId id;
+  std::memcpy(&id, unique_id128, sizeof(id));
+  NC(g_nccl.CommInitRank(&h->comm, n_ranks, id, rank));
+  h->n_ranks = n_ranks;
+  h->rank    = rank;
+  // learn every rank's shard with one tiny all-gather
+  int64_t* d_tab = nullptr;
+  CU(cudaMalloc(&d_tab, sizeof(int64_t) * 2 * n_ranks));
+  const int64_t mine[2] = {h->ds.shard_begin, h->ds.n};
+  CU(cudaMemcpyAsync(d_tab + 2 * rank, mine, sizeof(mine), cudaMemcpyHostToDevice, h->stream));
+  NC(g_nccl.AllGather(d_tab + 2 * rank, d_tab, 2, ncclInt64, h->comm, h->stream));
+  std::vector<int64_t> tab(2 * size_t(n_ranks));
+  CU(cudaMemcpyAsync(tab.data(), d_tab, sizeof(int64_t) * tab.size(), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  CU(cudaFree(d_tab));
+  h->shard_begin_of.assign(size_t(n_ranks), 0);
+  h->shard_count_of.assign(size_t(n_ranks), 0);
+  h->equal_shards = true;
+  int64_t covered = 0;
+  for (int r = 0; r < n_ranks; r++) {
+    h->shard_begin_of[size_t(r)] = tab[2 * size_t(r)];
+    h->shard_count_of[size_t(r)] = tab[2 * size_t(r) + 1];
+    covered += tab[2 * size_t(r) + 1];
+    if (tab[2 * size_t(r) + 1] != h->ds.n || tab[2 * size_t(r)] != int64_t(r) * h->ds.n) h->equal_shards = false;
+  }
+  if (covered != h->ds.n_global) return fail(MRSB_ERR_INVALID, "shards cover %lld UAVs, n_global is %lld", (long long)covered, (long long)h->ds.n_global);
+  return MRSB_OK;
+}
+
+int mrsb_gather_buffer(mrsb_handle h, void** device_ptr, size_t* bytes) {
+  GUARD(h);
+  if (device_ptr) *device_ptr = h->ds.gpos;
+  if (bytes) *bytes = sizeof(double) * 3 * size_t(h->ds.n_global);
+  return MRSB_OK;
+}
+
+int mrsb_publish_positions(mrsb_handle h) {
+  GUARD(h);
+  h->n_launches += launch_publish_positions(h->ds, h->stream);
+  CU(cudaGetLastError());
+  return MRSB_OK;
+}
+
+int mrsb_get_device_view(mrsb_handle h, mrsb_device_view* out) {
+  GUARD(h);
+  const int64_t ld = h->ds.ld;
+  out->ld          = ld;
+  out->x           = h->ds.st;
+  out->v           = h->ds.st + 3 * ld;
+  out->R           = h->ds.st + 6 * ld;
+  out->omega       = h->ds.st + 15 * ld;
+  out->motor_rpm   = h->ds.rpm;
+  out->imu_acc     = h->ds.imu;
+  out->ext_force   = h->ds.fext;
+  out->crashed     = reinterpret_cast<int32_t*>(h->ds.flags);
+  out->input_mode  = h->ds.mode;
+  return MRSB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,114 @@
+// internal.h — device data layout and host bookkeeping of libmrsb (not part of the public ABI).
+//
+// HBM layout: structure of arrays, one double array per state component with
+// leading dimension `ld` (n_local rounded up to 128), so thread i of a warp touches element i of
+// every component array: every load/store of the stepping kernel is a fully coalesced 256-byte
+// warp transaction.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/mrsb.h"
+
+#define MRSB_NM MRSB_MAX_MOTORS
+
+// per-UAV flag bits
+#define FLAG_CRASHED 1u        // UavSystem::crashed_ (US:80)
+#define FLAG_TAKEOFF 2u        // live copy of ModelParams::takeoff_patch_enabled (MM:275)
+#define FLAG_VPREV 4u          // v_prev array holds a value different from v (after set_state, MM:424-433)
+#define FLAG_FF_VEL_HDG_RATE 16u   // std::optional feed-forwards present (US:112-115)
+#define FLAG_FF_VEL_HDG 32u
+#define FLAG_FF_ACC_HDG_RATE 64u
+#define FLAG_FF_ACC_HDG 128u
+
+// rows of the command array (10 payload doubles + cached cos/sin of the heading)
+#define CMD_ROWS 12
+#define CMD_COS 10
+#define CMD_SIN 11
+// rows of the feed-forward array
+#define FF_VEL_HDG 0       // 3 rows
+#define FF_VEL_HDG_RATE 3  // 3 rows
+#define FF_ACC_HDG 6       // 3 rows
+#define FF_ACC_HDG_RATE 9  // 3 rows + heading_rate
+#define FF_ROWS 13
+// PID state rows: 2*k = last_error, 2*k+1 = integral; k = 0..2 position xyz, 3..5 velocity xyz,
+// 6..8 attitude xyz, 9..11 rate xyz
+#define PID_ROWS 24
+
+// One parameter set = one airframe + one set of controller gains, in the form the kernels want.
+// Derived on the host (params.cpp) from mrsb_model_params + mrsb_controller_params.
+struct DevParams {
+  int32_t n_motors;
+  int32_t ground_enabled;
+  int32_t mixer_desaturation;
+  int32_t j_diagonal;
+  double  g, mass, inv_mass, kf_n /* kf*n_motors */, min_rpm, rpm_range, inv_rpm_range, neg_inv_tau, air_k /* c*pi*l*l */, ground_z,
+      takeoff_rpm /* 0.9*hover_rpm, MM:266-267 */;
+  double arm_length, prop_radius;  // collision geometry (SIM:342)
+  double J[9], Jinv[9];            // row-major
+  double alloc[4][MRSB_NM];        // scaled allocation matrix rows: torque xyz, thrust
+  double mix[MRSB_NM][4];          // normalised pseudo-inverse (CTL/mixer.hpp:72-101)
+  double pos_kp, pos_kd, pos_ki, pos_sat;
+  double vel_kp, vel_kd, vel_ki, vel_sat;
+  double att_kp, att_kd, att_ki, att_sat_rp, att_sat_yaw;
+  double rate_kp[3], rate_kd[3], rate_ki[3];  // already multiplied by J_ii (CTL/rate_controller.hpp:62-64)
+};
+
+// Device pointers of one shard.  Passed to kernels by value.
+struct DevState {
+  int64_t  n;   // UAVs in this shard
+  int64_t  ld;  // leading dimension of all SoA arrays
+  double*  st;  // [18][ld] x(0-2) v(3-5) R col-major(6-14) omega(15-17)  == InternalState MM:204-214
+  double*  vprev;  // [3][ld]  only meaningful where FLAG_VPREV is set
+  double*  rpm;    // [MRSB_NM][ld]
+  double*  pid;    // [PID_ROWS][ld]
+  double*  fext;   // [3][ld] external_force_  (MM:142)
+  double*  mext;   // [3][ld] external_moment_ (MM:143)
+  double*  imu;    // [3][ld] imu_acceleration_ (MM:139)
+  double*  initz;  // [ld] _initial_pos_.z (MM:145; only z is ever read, MM:269-270)
+  double*  cmd;    // [CMD_ROWS][ld]
+  double*  ff;     // [FF_ROWS][ld]
+  uint32_t* flags;  // [ld]
+  uint8_t*  mode;   // [ld] INPUT_MODE (US:95)
+  const int32_t* pset;  // [n_global] parameter-set index of every UAV of the swarm (local ones at +shard_begin)
+  const DevParams* params;
+  double*  gpos;  // [n_global][3] packed positions: this shard's slice is written by the step kernel
+  int64_t  shard_begin;
+  int64_t  n_global;
+};
+
+// collision pass workspace
+struct DevGrid {
+  uint32_t  n_buckets;  // power of two
+  uint32_t  bits;
+  uint32_t* keys;       // [n_global] bucket of each UAV
+  uint32_t* keys_sorted;
+  uint32_t* vals;       // [n_global] iota
+  uint32_t* vals_sorted;
+  uint32_t* begin;      // [n_buckets+1] first sorted slot of each bucket
+  double4*  rec;        // [n_global] sorted records {x,y,z, index bits}
+  int32_t*  pairs;      // [pair_cap][2]
+  int64_t   pair_cap;
+  unsigned long long* counters;  // [0] pairs found by the last pass
+};
+
+// kernel launchers (step_kernel.cu / collide.cu / io_kernels.cu); all return the number of launches made
+int launch_step(const DevState& s, double dt, int k_substeps, int uniform_mode, int uniform_nm, bool any_moment, cudaStream_t stream);
+int launch_collide(const DevState& s, const DevGrid& g, int crash_mode, double rebounce, void* cub_tmp, size_t cub_tmp_bytes, cudaStream_t stream);
+size_t collide_tmp_bytes(int64_t n_global);
+int launch_publish_positions(const DevState& s, cudaStream_t stream);
+
+int launch_scatter_input(const DevState& s, int mode, int64_t n, const int32_t* idx_dev, const double* payload_dev, int stride, cudaStream_t stream);
+int launch_scatter_rows(double* dst, int64_t ld, int rows, int64_t n, const int32_t* idx_dev, const double* payload_dev, int stride, int col0,
+                        cudaStream_t stream);
+int launch_gather_rows(const double* src, int64_t ld, int rows, int64_t n, const int32_t* idx_dev, double* out_dev, int stride, int col0,
+                       cudaStream_t stream);
+int launch_flag_update(const DevState& s, int64_t n, const int32_t* idx_dev, uint32_t and_mask, uint32_t or_mask, cudaStream_t stream);
+int launch_gather_u32(const uint32_t* src, int64_t n, const int32_t* idx_dev, uint32_t* out_dev, cudaStream_t stream);
+int launch_gather_u8(const uint8_t* src, int64_t n, const int32_t* idx_dev, int32_t* out_dev, cudaStream_t stream);
+int launch_set_mode(const DevState& s, int64_t n, const int32_t* idx_dev, int mode, cudaStream_t stream);
+int launch_set_state_pos(const DevState& s, int64_t n, const int32_t* idx_dev, const double* xyz_dev, const double* hdg_dev, cudaStream_t stream);
+int launch_stash_vprev(const DevState& s, int64_t n, const int32_t* idx_dev, cudaStream_t stream);
+int launch_gather_vprev(const DevState& s, int64_t n, const int32_t* idx_dev, double* out_dev, cudaStream_t stream);
+int launch_reset_pid(const DevState& s, int64_t n, const int32_t* idx_dev, int row0, int rows, cudaStream_t stream);
+int launch_set_pset(int32_t* pset_dev, int64_t n, const int32_t* idx_dev, int64_t offset, const int32_t* values_dev, cudaStream_t stream);

@@ -1,0 +1,657 @@
+// step_kernel.cu — K1: fused controller cascade + mixer + motor lag + RK4 rigid body + post-step,
+// for K consecutive makeStep(dt) calls per launch.  One thread per UAV, FP64, state in registers.
+//
+// What it computes, per UAV and per substep, is exactly UavSystem::makeStep (US:304-380):
+//   cascade  Position -> Velocity -> Acceleration -> Attitude/Tilt -> Rate -> Mixer   (CTL/*.hpp)
+//   MultirotorModel::setInput (MM:392-410), MultirotorModel::step (MM:220-286) with the
+//   derivative MM:301-366 and odeint's classic RK4 (ODE/stepper/runge_kutta4.hpp:42-95).
+// How it computes it is new (this is not a transcription):
+//   * the re-orthonormalisation R*chol(R^T R)^-1 (MM:314-316, 249-253) uses the closed-form
+//     inverse of the lower-triangular factor and three rsqrt, not a general 3x3 cofactor inverse
+//     (17 divisions + 7 sqrt per derivative in the reference -> 4 rsqrt here);
+//   * thrust/torque from the motor speeds and F_ext/m are hoisted out of the four RK stages
+//     (the reference recomputes them from the frozen members every stage, MM:332-335, 346);
+//   * drag c*pi*l^2*|v|^2 * v/|v| / m collapses to (c*pi*l^2/m)*|v| * v;
+//   * the oblique projection of the heading vector (CTL/acceleration_controller.hpp:60-80,
+//     seven dynamic matrices and a 2x2 LU) is its closed form (cos h, sin h, -(nx cos h+ny sin h)/nz);
+//   * the SO(3) error needs only the six off-diagonal dot products of Rd^T R;
+//   * RK4 keeps a running weighted sum instead of four stored slopes, and skips the zero-
+//     coefficient terms odeint multiplies through (generic_rk_operations.hpp:30-68);
+//   * FMA contraction is on.
+// All of these change results only at rounding level (<= a few ulp per operation); parity with the
+// CPU oracle is asserted within the tolerances of DESIGN.md §5 by tests/test_step_parity.py.
+//
+// Roofline: ~0.4-0.8 kB of state traffic and ~2.6 kFLOP (as-written census) per
+// UAV-step; FP64-pipe bound on B200 once K >= 2, close to balanced at K = 1.
+#include "internal.h"
+
+namespace {
+
+#define DEV __device__ __forceinline__
+
+struct Vec3 {
+  double x, y, z;
+};
+DEV Vec3 mk(double x, double y, double z) {
+  Vec3 r;
+  r.x = x;
+  r.y = y;
+  r.z = z;
+  return r;
+}
+DEV Vec3   operator+(Vec3 a, Vec3 b) { return mk(a.x + b.x, a.y + b.y, a.z + b.z); }
+DEV Vec3   operator-(Vec3 a, Vec3 b) { return mk(a.x - b.x, a.y - b.y, a.z - b.z); }
+DEV Vec3   operator*(Vec3 a, double s) { return mk(a.x * s, a.y * s, a.z * s); }
+DEV double dot(Vec3 a, Vec3 b) { return a.x * b.x + (a.y * b.y + a.z * b.z); }
+DEV Vec3   cross(Vec3 a, Vec3 b) { return mk(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+DEV Vec3   fma3(Vec3 a, double s, Vec3 b) { return mk(fma(a.x, s, b.x), fma(a.y, s, b.y), fma(a.z, s, b.z)); }  // a*s + b
+// Eigen normalized(): divide by the norm only if the squared norm is positive
+DEV Vec3 normalized(Vec3 a) {
+  const double z = dot(a, a);
+  if (z > 0.0) {
+    const double r = 1.0 / sqrt(z);
+    return a * r;
+  }
+  return a;
+}
+DEV bool isnan3(Vec3 a) { return (a.x != a.x) | (a.y != a.y) | (a.z != a.z); }
+DEV Vec3 nan0(Vec3 a) { return mk(a.x != a.x ? 0.0 : a.x, a.y != a.y ? 0.0 : a.y, a.z != a.z ? 0.0 : a.z); }
+
+struct Rot {
+  Vec3 c0, c1, c2;  // columns
+};
+
+// R * chol(R^T R)^-1  with chol = lower Cholesky factor (MM:314-316 / MM:249-253).
+DEV Rot reortho(const Rot& R) {
+  const double g00 = dot(R.c0, R.c0), g10 = dot(R.c1, R.c0), g20 = dot(R.c2, R.c0);
+  const double g11 = dot(R.c1, R.c1), g21 = dot(R.c2, R.c1), g22 = dot(R.c2, R.c2);
+  const double i00 = rsqrt(g00);
+  const double l10 = g10 * i00, l20 = g20 * i00;
+  const double d1  = g11 - l10 * l10;
+  const double i11 = rsqrt(d1);
+  const double l11 = d1 * i11;
+  const double l21 = (g21 - l20 * l10) * i11;
+  const double d2  = g22 - (l20 * l20 + l21 * l21);
+  const double i22 = rsqrt(d2);
+  const double a10 = -(l10 * i00) * i11;
+  const double a21 = -(l21 * i11) * i22;
+  const double a20 = (l10 * l21 - l20 * l11) * (i00 * i11 * i22);
+  Rot          N;
+  N.c0 = fma3(R.c2, a20, fma3(R.c1, a10, R.c0 * i00));
+  N.c1 = fma3(R.c2, a21, R.c1 * i11);
+  N.c2 = R.c2 * i22;
+  return N;
+}
+
+// quantities frozen over the four RK stages of one step (MM:332-350: members, not ODE state)
+struct Frozen {
+  double g;
+  double thrust_m;  // thrust / mass
+  double air_m;     // c*pi*l^2 / mass
+  Vec3   f_m;       // F_ext / mass
+  Vec3   tau;       // allocation torque + external moment
+};
+
+struct Slope {
+  Vec3 dv, dw;
+  Rot  dR;
+};
+
+// MultirotorModel::operator() (MM:301-366) without the x_dot = v rows (handled by the caller)
+DEV Slope derivative(Vec3 v, const Rot& Rraw, Vec3 w, const Frozen& f, const DevParams* __restrict__ P, bool jdiag, Vec3 Jd, Vec3 Jdi) {
+  Slope      k;
+  const Rot  R  = reortho(Rraw);
+  const double vv    = dot(v, v);
+  const double speed = vv > 0.0 ? vv * rsqrt(vv) : 0.0;
+  const double kd    = f.air_m * speed;
+  k.dv = mk(fma(R.c2.x, f.thrust_m, f.f_m.x) - kd * v.x, fma(R.c2.y, f.thrust_m, f.f_m.y) - kd * v.y,
+            (fma(R.c2.z, f.thrust_m, f.f_m.z) - f.g) - kd * v.z);
+  // R * [w]x
+  k.dR.c0 = R.c1 * w.z - R.c2 * w.y;
+  k.dR.c1 = R.c2 * w.x - R.c0 * w.z;
+  k.dR.c2 = R.c0 * w.y - R.c1 * w.x;
+  if (jdiag) {
+    const Vec3 Jw = mk(Jd.x * w.x, Jd.y * w.y, Jd.z * w.z);
+    const Vec3 r  = f.tau - cross(w, Jw);
+    k.dw          = mk(r.x * Jdi.x, r.y * Jdi.y, r.z * Jdi.z);
+  } else {
+    const double* J  = P->J;
+    const double* Ji = P->Jinv;
+    const Vec3    Jw = mk(J[0] * w.x + (J[1] * w.y + J[2] * w.z), J[3] * w.x + (J[4] * w.y + J[5] * w.z), J[6] * w.x + (J[7] * w.y + J[8] * w.z));
+    const Vec3    r  = f.tau - cross(w, Jw);
+    k.dw = mk(Ji[0] * r.x + (Ji[1] * r.y + Ji[2] * r.z), Ji[3] * r.x + (Ji[4] * r.y + Ji[5] * r.z), Ji[6] * r.x + (Ji[7] * r.y + Ji[8] * r.z));
+  }
+  // MM:361-365
+  k.dv    = nan0(k.dv);
+  k.dw    = nan0(k.dw);
+  k.dR.c0 = nan0(k.dR.c0);
+  k.dR.c1 = nan0(k.dR.c1);
+  k.dR.c2 = nan0(k.dR.c2);
+  return k;
+}
+
+// PIDController::update (CTL/pid.hpp:67-96)
+DEV double pid(double e, double dt, double inv_dt, double kp, double kd, double ki, double sat, double aw, double& last, double& integ) {
+  const double diff = (e - last) * inv_dt;
+  last              = e;
+  double u          = kp * e + kd * diff + ki * integ;
+  if (sat > 0.0) {
+    if (u >= sat) {
+      u = sat;
+    } else if (u <= -sat) {
+      u = -sat;
+    }
+  }
+  if (aw > 0.0 && fabs(u) < aw) integ += e * dt;
+  return u;
+}
+
+DEV int signum(double v) { return (0.0 < v) - (v < 0.0); }
+
+// attitude error vee( 1/2 (Rd^T R - R^T Rd) ) / 2  (CTL/attitude_controller.hpp:82-89)
+DEV Vec3 attitude_error(const Rot& Rd, const Rot& R) {
+  const double a12 = dot(Rd.c1, R.c2), a21 = dot(Rd.c2, R.c1);
+  const double a20 = dot(Rd.c2, R.c0), a02 = dot(Rd.c0, R.c2);
+  const double a01 = dot(Rd.c0, R.c1), a10 = dot(Rd.c1, R.c0);
+  return mk((a12 - a21) * 0.5, (a20 - a02) * 0.5, (a01 - a10) * 0.5);
+}
+
+template <int NM_T, int MODE_T>
+__global__ void __launch_bounds__(128) uav_step_kernel(DevState s, double dt, int k_sub, int any_moment) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= s.n) return;
+  const int64_t ld = s.ld;
+
+  const DevParams* __restrict__ P = s.params + s.pset[s.shard_begin + i];
+  const int nm                    = NM_T > 0 ? NM_T : P->n_motors;
+  const int mode0                 = MODE_T >= 0 ? MODE_T : int(s.mode[i]);
+  uint32_t  flags                 = s.flags[i];
+
+#define LD(arr, row) (arr)[int64_t(row) * ld + i]
+
+  // ---- load state -------------------------------------------------------------------------
+  Vec3 x = mk(LD(s.st, 0), LD(s.st, 1), LD(s.st, 2));
+  Vec3 v = mk(LD(s.st, 3), LD(s.st, 4), LD(s.st, 5));
+  Rot  R;
+  R.c0   = mk(LD(s.st, 6), LD(s.st, 7), LD(s.st, 8));
+  R.c1   = mk(LD(s.st, 9), LD(s.st, 10), LD(s.st, 11));
+  R.c2   = mk(LD(s.st, 12), LD(s.st, 13), LD(s.st, 14));
+  Vec3 w = mk(LD(s.st, 15), LD(s.st, 16), LD(s.st, 17));
+  double rpm[MRSB_NM];
+#pragma unroll
+  for (int m = 0; m < MRSB_NM; m++) rpm[m] = (m < nm) ? LD(s.rpm, m) : 0.0;
+  Vec3 vprev = v;
+  if (flags & FLAG_VPREV) vprev = mk(LD(s.vprev, 0), LD(s.vprev, 1), LD(s.vprev, 2));
+  const Vec3 fext = mk(LD(s.fext, 0), LD(s.fext, 1), LD(s.fext, 2));
+  Vec3       mext = mk(0, 0, 0);
+  if (any_moment) mext = mk(LD(s.mext, 0), LD(s.mext, 1), LD(s.mext, 2));
+
+  const bool live = !(flags & FLAG_CRASHED) && mode0 != MRSB_INPUT_UNKNOWN;  // US:308
+  // which controllers are on this UAV's path (decides which PID rows are touched)
+  const bool on_pos  = live && mode0 == MRSB_POSITION_CMD;
+  const bool on_vel  = live && mode0 >= MRSB_VELOCITY_HDG_RATE_CMD;
+  const bool on_att  = live && mode0 >= MRSB_ATTITUDE_CMD;
+  const bool on_rate = live && mode0 >= MRSB_ATTITUDE_RATE_CMD;
+
+  double pd[PID_ROWS];
+#pragma unroll
+  for (int r = 0; r < 6; r++) pd[r] = on_pos ? LD(s.pid, r) : 0.0;
+#pragma unroll
+  for (int r = 6; r < 12; r++) pd[r] = on_vel ? LD(s.pid, r) : 0.0;
+#pragma unroll
+  for (int r = 12; r < 18; r++) pd[r] = on_att ? LD(s.pid, r) : 0.0;
+#pragma unroll
+  for (int r = 18; r < 24; r++) pd[r] = on_rate ? LD(s.pid, r) : 0.0;
+
+  // command payload
+  double c[CMD_ROWS];
+#pragma unroll
+  for (int r = 0; r < CMD_ROWS; r++) c[r] = 0.0;
+  if (live) {
+    if (mode0 == MRSB_ACTUATOR_CMD) {
+#pragma unroll
+      for (int m = 0; m < MRSB_NM; m++)
+        if (m < nm) c[m] = LD(s.cmd, m);
+    } else if (mode0 == MRSB_ATTITUDE_CMD) {
+#pragma unroll
+      for (int r = 0; r < 10; r++) c[r] = LD(s.cmd, r);
+    } else {
+#pragma unroll
+      for (int r = 0; r < 4; r++) c[r] = LD(s.cmd, r);
+      if (mode0 == MRSB_TILT_HDG_RATE_CMD) c[4] = LD(s.cmd, 4);
+      if (mode0 == MRSB_POSITION_CMD || mode0 == MRSB_VELOCITY_HDG_CMD || mode0 == MRSB_ACCELERATION_HDG_CMD) {
+        c[CMD_COS] = LD(s.cmd, CMD_COS);
+        c[CMD_SIN] = LD(s.cmd, CMD_SIN);
+      }
+    }
+  }
+  // sticky feed-forwards (US:318-346)
+  Vec3   ff_vel = mk(0, 0, 0), ff_acc = mk(0, 0, 0);
+  double ff_hdg_rate = 0.0;
+  if (on_pos) {
+    if (flags & FLAG_FF_VEL_HDG) {
+      ff_vel = mk(LD(s.ff, FF_VEL_HDG + 0), LD(s.ff, FF_VEL_HDG + 1), LD(s.ff, FF_VEL_HDG + 2));
+    } else if (flags & FLAG_FF_VEL_HDG_RATE) {
+      ff_vel = mk(LD(s.ff, FF_VEL_HDG_RATE + 0), LD(s.ff, FF_VEL_HDG_RATE + 1), LD(s.ff, FF_VEL_HDG_RATE + 2));
+    }
+  }
+  if (on_vel) {
+    const bool hdg_branch = mode0 != MRSB_VELOCITY_HDG_RATE_CMD;  // POSITION and VELOCITY_HDG go through ACCELERATION_HDG
+    const bool has_a      = flags & FLAG_FF_ACC_HDG;
+    const bool has_ar     = flags & FLAG_FF_ACC_HDG_RATE;
+    // hdg branch: acc_hdg first, else acc_hdg_rate (US:330-334); rate branch: acc_hdg_rate first (+heading_rate), else acc_hdg (US:341-346)
+    const bool use_ar = hdg_branch ? (!has_a && has_ar) : has_ar;
+    const bool use_a  = hdg_branch ? has_a : (!has_ar && has_a);
+    if (use_a) ff_acc = mk(LD(s.ff, FF_ACC_HDG + 0), LD(s.ff, FF_ACC_HDG + 1), LD(s.ff, FF_ACC_HDG + 2));
+    if (use_ar) {
+      ff_acc = mk(LD(s.ff, FF_ACC_HDG_RATE + 0), LD(s.ff, FF_ACC_HDG_RATE + 1), LD(s.ff, FF_ACC_HDG_RATE + 2));
+      if (!hdg_branch) ff_hdg_rate = LD(s.ff, FF_ACC_HDG_RATE + 3);
+    }
+  }
+  const double initz = (flags & FLAG_TAKEOFF) ? s.initz[i] : 0.0;
+
+  // ---- per-launch constants ---------------------------------------------------------------
+  const double inv_dt   = 1.0 / dt;
+  const double filt     = exp(dt * P->neg_inv_tau);  // MM:244
+  const double inv_mass = P->inv_mass;
+  const double g        = P->g;
+  const bool   jdiag    = P->j_diagonal != 0;
+  const Vec3   Jd       = mk(P->J[0], P->J[4], P->J[8]);
+  const Vec3   Jdi      = mk(P->Jinv[0], P->Jinv[4], P->Jinv[8]);
+  const double min_rpm = P->min_rpm, rpm_range = P->rpm_range;
+
+  Vec3 imu = mk(0, 0, 0);
+
+  for (int sub = 0; sub < k_sub; sub++) {
+    // ======================= controller cascade (US:304-374) =================================
+    double u[MRSB_NM];
+#pragma unroll
+    for (int m = 0; m < MRSB_NM; m++) u[m] = 0.0;
+
+    if (live) {
+      int    mode = mode0;
+      Vec3   vec  = mk(c[0], c[1], c[2]);  // position / velocity / acceleration / tilt / rates / roll-pitch-yaw
+      double sc   = c[3];                  // heading | heading_rate | throttle
+      double throttle = 0.0;
+      Rot    Rd;
+      Rd.c0 = Rd.c1 = Rd.c2 = mk(0, 0, 0);
+
+      if (mode == MRSB_POSITION_CMD) {  // CTL/position_controller.hpp:73-86
+        const Vec3   e   = vec - x;
+        const double sat = P->pos_sat;
+        vec.x = pid(e.x, dt, inv_dt, P->pos_kp, P->pos_kd, P->pos_ki, sat, 1.0, pd[0], pd[1]);
+        vec.y = pid(e.y, dt, inv_dt, P->pos_kp, P->pos_kd, P->pos_ki, sat, 1.0, pd[2], pd[3]);
+        vec.z = pid(e.z, dt, inv_dt, P->pos_kp, P->pos_kd, P->pos_ki, sat, 1.0, pd[4], pd[5]);
+        vec   = vec + ff_vel;
+        mode  = MRSB_VELOCITY_HDG_CMD;
+      }
+      if (mode == MRSB_VELOCITY_HDG_CMD || mode == MRSB_VELOCITY_HDG_RATE_CMD) {  // CTL/velocity_controller.hpp:68-102
+        const Vec3   e   = vec - v;
+        const double sat = P->vel_sat;
+        vec.x = pid(e.x, dt, inv_dt, P->vel_kp, P->vel_kd, P->vel_ki, sat, 1.0, pd[6], pd[7]);
+        vec.y = pid(e.y, dt, inv_dt, P->vel_kp, P->vel_kd, P->vel_ki, sat, 1.0, pd[8], pd[9]);
+        vec.z = pid(e.z, dt, inv_dt, P->vel_kp, P->vel_kd, P->vel_ki, sat, 1.0, pd[10], pd[11]);
+        vec   = vec + ff_acc;
+        sc += ff_hdg_rate;
+        mode = (mode == MRSB_VELOCITY_HDG_CMD) ? MRSB_ACCELERATION_HDG_CMD : MRSB_ACCELERATION_HDG_RATE_CMD;
+      }
+      if (mode == MRSB_ACCELERATION_HDG_CMD || mode == MRSB_ACCELERATION_HDG_RATE_CMD) {  // CTL/acceleration_controller.hpp:44-122
+        const double mass = P->mass;
+        const Vec3   fd   = mk(vec.x * mass, vec.y * mass, (vec.z + g) * mass);
+        const Vec3   n    = normalized(fd);
+        const double tf   = dot(fd, R.c2);
+        throttle          = (sqrt(tf / P->kf_n) - min_rpm) * P->inv_rpm_range;
+        if (mode == MRSB_ACCELERATION_HDG_CMD) {
+          const double ch = c[CMD_COS], sh = c[CMD_SIN];
+          const double num = n.x * ch + n.y * sh;
+          const double z3  = (num == 0.0) ? 0.0 : -num / n.z;
+          Rd.c2            = n;
+          Rd.c0            = normalized(mk(ch, sh, z3));
+          Rd.c1            = normalized(cross(Rd.c2, Rd.c0));
+          mode             = MRSB_ATTITUDE_CMD;
+        } else {
+          vec  = n;  // tilt vector; sc stays the heading rate
+          mode = MRSB_TILT_HDG_RATE_CMD;
+        }
+      } else if (mode == MRSB_ATTITUDE_CMD) {
+        Rd.c0    = mk(c[0], c[1], c[2]);
+        Rd.c1    = mk(c[3], c[4], c[5]);
+        Rd.c2    = mk(c[6], c[7], c[8]);
+        throttle = c[9];
+      } else if (mode == MRSB_TILT_HDG_RATE_CMD) {
+        throttle = c[4];
+      } else {
+        throttle = c[3];  // ATTITUDE_RATE / CONTROL_GROUP
+      }
+
+      if (mode == MRSB_ATTITUDE_CMD || mode == MRSB_TILT_HDG_RATE_CMD) {  // CTL/attitude_controller.hpp:79-145
+        const bool tilt = (mode == MRSB_TILT_HDG_RATE_CMD);
+        if (tilt) {
+          Rd.c2 = normalized(vec);
+          Rd.c1 = normalized(cross(Rd.c2, R.c0));
+          Rd.c0 = normalized(cross(Rd.c1, Rd.c2));
+        }
+        const Vec3 e = attitude_error(Rd, R);
+        double rx = pid(e.x, dt, inv_dt, P->att_kp, P->att_kd, P->att_ki, P->att_sat_rp, 0.1, pd[12], pd[13]);
+        double ry = pid(e.y, dt, inv_dt, P->att_kp, P->att_kd, P->att_ki, P->att_sat_rp, 0.1, pd[14], pd[15]);
+        double rz = pid(e.z, dt, inv_dt, P->att_kp, P->att_kd, P->att_ki, P->att_sat_yaw, 0.1, pd[16], pd[17]);
+        if (tilt) {
+          // intrinsicBodyRateToHeadingRate (:177-206): d/dt atan2(R10, R00) under body rates (rx,ry,rz)
+          const double rd00 = R.c1.x * rz - R.c2.x * ry;  // (R*[w]x)(0,0)
+          const double rd10 = R.c1.y * rz - R.c2.y * ry;  // (R*[w]x)(1,0)
+          const double hx = R.c0.x, hy = R.c0.y;
+          const double den = hx * hx + hy * hy;
+          double       parasitic = 0.0;
+          if (!(fabs(den) <= 1e-5)) parasitic = (-hy / den) * rd00 + (hx / den) * rd10;
+          // getYawRateIntrinsic (:212-251)
+          const double hr  = sc - parasitic;
+          double       yaw = 0.0;
+          if (!(fabs(hr) < 1e-3)) {
+            const Vec3   orb  = mk(-hr * hy, hr * hx, 0.0);
+            const Vec3   b    = normalized(mk(-hy, hx, 0.0));
+            const double bp   = b.x * R.c1.x + (b.y * R.c1.y + b.z * R.c1.z);
+            const Vec3   proj = b * bp;
+            const double on = sqrt(dot(orb, orb)), pn = sqrt(dot(proj, proj));
+            if (!(fabs(pn) < 1e-5)) {
+              const double o = double(signum(dot(orb, proj))) * (on / pn);
+              yaw            = isfinite(o) ? o : 0.0;
+            }
+          }
+          rz += yaw;
+        }
+        vec  = mk(rx, ry, rz);
+        mode = MRSB_ATTITUDE_RATE_CMD;
+      }
+      if (mode == MRSB_ATTITUDE_RATE_CMD) {  // CTL/rate_controller.hpp:67-81
+        const Vec3 e = vec - w;
+        vec.x = pid(e.x, dt, inv_dt, P->rate_kp[0], P->rate_kd[0], P->rate_ki[0], -1.0, 1.0, pd[18], pd[19]);
+        vec.y = pid(e.y, dt, inv_dt, P->rate_kp[1], P->rate_kd[1], P->rate_ki[1], -1.0, 1.0, pd[20], pd[21]);
+        vec.z = pid(e.z, dt, inv_dt, P->rate_kp[2], P->rate_kd[2], P->rate_ki[2], -1.0, 1.0, pd[22], pd[23]);
+        mode  = MRSB_CONTROL_GROUP_CMD;
+      }
+      if (mode == MRSB_CONTROL_GROUP_CMD) {  // CTL/mixer.hpp:107-144
+        double mn = 1e300, mx = -1e300, sum = 0.0;
+#pragma unroll
+        for (int m = 0; m < MRSB_NM; m++) {
+          if (m < nm) {
+            u[m] = (P->mix[m][0] * vec.x + P->mix[m][1] * vec.y) + (P->mix[m][2] * vec.z + P->mix[m][3] * throttle);
+            mn   = fmin(mn, u[m]);
+          }
+        }
+        if (P->mixer_desaturation) {
+          // fmin/fmax drop NaN operands; Eigen's minCoeff/maxCoeff comparisons also never select a NaN after a number
+          if (mn < 0.0) {
+            const double sh = fabs(mn);
+#pragma unroll
+            for (int m = 0; m < MRSB_NM; m++)
+              if (m < nm) u[m] += sh;
+          }
+#pragma unroll
+          for (int m = 0; m < MRSB_NM; m++)
+            if (m < nm) {
+              mx = fmax(mx, u[m]);
+              sum += u[m];
+            }
+          if (mx > 1.0) {
+            if (throttle > 1e-2) {
+              const double sc2 = (sum / double(nm)) / throttle;
+              const double r0 = vec.x / sc2, r1 = vec.y / sc2, r2 = vec.z / sc2;
+#pragma unroll
+              for (int m = 0; m < MRSB_NM; m++)
+                if (m < nm) u[m] = (P->mix[m][0] * r0 + P->mix[m][1] * r1) + (P->mix[m][2] * r2 + P->mix[m][3] * throttle);
+            } else {
+#pragma unroll
+              for (int m = 0; m < MRSB_NM; m++)
+                if (m < nm) u[m] /= mx;
+            }
+          }
+        }
+      } else {  // ACTUATOR_CMD
+#pragma unroll
+        for (int m = 0; m < MRSB_NM; m++) u[m] = c[m];
+      }
+    }
+
+    // ======================= MultirotorModel::setInput (MM:392-410) ==========================
+    double usum = 0.0;
+#pragma unroll
+    for (int m = 0; m < MRSB_NM; m++) {
+      if (m < nm) {
+        double val = u[m];
+        if (!isfinite(val)) val = 0.0;
+        val  = val < 0.0 ? 0.0 : (val > 1.0 ? 1.0 : val);
+        u[m] = fma(rpm_range, val, min_rpm);
+        usum += u[m];
+      }
+    }
+
+    // ======================= MultirotorModel::step (MM:220-286) ==============================
+    Frozen fz;
+    {
+      double t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+#pragma unroll
+      for (int m = 0; m < MRSB_NM; m++) {
+        if (m < nm) {
+          const double sq = rpm[m] * rpm[m];
+          t0 = fma(P->alloc[0][m], sq, t0);
+          t1 = fma(P->alloc[1][m], sq, t1);
+          t2 = fma(P->alloc[2][m], sq, t2);
+          t3 = fma(P->alloc[3][m], sq, t3);
+        }
+      }
+      fz.g        = g;
+      fz.thrust_m = t3 * inv_mass;
+      fz.air_m    = P->air_k * inv_mass;
+      fz.f_m      = fext * inv_mass;
+      fz.tau      = mk(t0, t1, t2) + mext;
+    }
+
+    // classic RK4, running weighted sum
+    const double h = 0.5 * dt;
+    Slope        k = derivative(v, R, w, fz, P, jdiag, Jd, Jdi);
+    Vec3         sx = v, sv = k.dv, sw = k.dw;
+    Rot          sR = k.dR;
+    Vec3         vt = fma3(k.dv, h, v), wt = fma3(k.dw, h, w);
+    Rot          Rt;
+    Rt.c0 = fma3(k.dR.c0, h, R.c0);
+    Rt.c1 = fma3(k.dR.c1, h, R.c1);
+    Rt.c2 = fma3(k.dR.c2, h, R.c2);
+
+    k  = derivative(vt, Rt, wt, fz, P, jdiag, Jd, Jdi);
+    sx = fma3(vt, 2.0, sx);
+    sv = fma3(k.dv, 2.0, sv);
+    sw = fma3(k.dw, 2.0, sw);
+    sR.c0 = fma3(k.dR.c0, 2.0, sR.c0);
+    sR.c1 = fma3(k.dR.c1, 2.0, sR.c1);
+    sR.c2 = fma3(k.dR.c2, 2.0, sR.c2);
+    vt    = fma3(k.dv, h, v);
+    wt    = fma3(k.dw, h, w);
+    Rt.c0 = fma3(k.dR.c0, h, R.c0);
+    Rt.c1 = fma3(k.dR.c1, h, R.c1);
+    Rt.c2 = fma3(k.dR.c2, h, R.c2);
+
+    k  = derivative(vt, Rt, wt, fz, P, jdiag, Jd, Jdi);
+    sx = fma3(vt, 2.0, sx);
+    sv = fma3(k.dv, 2.0, sv);
+    sw = fma3(k.dw, 2.0, sw);
+    sR.c0 = fma3(k.dR.c0, 2.0, sR.c0);
+    sR.c1 = fma3(k.dR.c1, 2.0, sR.c1);
+    sR.c2 = fma3(k.dR.c2, 2.0, sR.c2);
+    vt    = fma3(k.dv, dt, v);
+    wt    = fma3(k.dw, dt, w);
+    Rt.c0 = fma3(k.dR.c0, dt, R.c0);
+    Rt.c1 = fma3(k.dR.c1, dt, R.c1);
+    Rt.c2 = fma3(k.dR.c2, dt, R.c2);
+
+    k  = derivative(vt, Rt, wt, fz, P, jdiag, Jd, Jdi);
+    sx = sx + vt;
+    sv = sv + k.dv;
+    sw = sw + k.dw;
+    sR.c0 = sR.c0 + k.dR.c0;
+    sR.c1 = sR.c1 + k.dR.c1;
+    sR.c2 = sR.c2 + k.dR.c2;
+
+    const double h6 = dt * (1.0 / 6.0);
+    const Vec3   xn = fma3(sx, h6, x), vn = fma3(sv, h6, v), wn = fma3(sw, h6, w);
+    Rot          Rn;
+    Rn.c0 = fma3(sR.c0, h6, R.c0);
+    Rn.c1 = fma3(sR.c1, h6, R.c1);
+    Rn.c2 = fma3(sR.c2, h6, R.c2);
+
+    // MM:228-233: any NaN -> keep the pre-step state
+    const bool bad = isnan3(xn) | isnan3(vn) | isnan3(wn) | isnan3(Rn.c0) | isnan3(Rn.c1) | isnan3(Rn.c2);
+    if (!bad) {
+      x = xn;
+      v = vn;
+      w = wn;
+      R = Rn;
+    }
+
+    // MM:244-246 first-order motor lag, outside the ODE
+#pragma unroll
+    for (int m = 0; m < MRSB_NM; m++)
+      if (m < nm) rpm[m] = filt * rpm[m] + (1.0 - filt) * u[m];
+
+    R = reortho(R);  // MM:249-253
+
+    if (P->ground_enabled) {  // MM:256-262
+      if (x.z < P->ground_z && v.z < 0.0) {
+        x.z = P->ground_z;
+        v   = mk(0, 0, 0);
+        w   = mk(0, 0, 0);
+      }
+    }
+    if (flags & FLAG_TAKEOFF) {  // MM:264-277
+      if (usum / double(nm) <= P->takeoff_rpm) {
+        if (x.z < initz && v.z < 0.0) {
+          x.z = initz;
+          v   = mk(0, 0, 0);
+          w   = mk(0, 0, 0);
+        }
+      } else {
+        flags &= ~FLAG_TAKEOFF;
+      }
+    }
+
+    // MM:280-281 fabricated accelerometer
+    const Vec3 lin = mk((v.x - vprev.x) * inv_dt, (v.y - vprev.y) * inv_dt, (v.z - vprev.z) * inv_dt + g);
+    imu            = mk(dot(R.c0, lin), dot(R.c1, lin), dot(R.c2, lin));
+    vprev          = v;
+  }
+
+  // ---- store ------------------------------------------------------------------------------
+#define ST(arr, row, val) (arr)[int64_t(row) * ld + i] = (val)
+  ST(s.st, 0, x.x);
+  ST(s.st, 1, x.y);
+  ST(s.st, 2, x.z);
+  ST(s.st, 3, v.x);
+  ST(s.st, 4, v.y);
+  ST(s.st, 5, v.z);
+  ST(s.st, 6, R.c0.x);
+  ST(s.st, 7, R.c0.y);
+  ST(s.st, 8, R.c0.z);
+  ST(s.st, 9, R.c1.x);
+  ST(s.st, 10, R.c1.y);
+  ST(s.st, 11, R.c1.z);
+  ST(s.st, 12, R.c2.x);
+  ST(s.st, 13, R.c2.y);
+  ST(s.st, 14, R.c2.z);
+  ST(s.st, 15, w.x);
+  ST(s.st, 16, w.y);
+  ST(s.st, 17, w.z);
+#pragma unroll
+  for (int m = 0; m < MRSB_NM; m++)
+    if (m < nm) ST(s.rpm, m, rpm[m]);
+  if (on_pos) {
+#pragma unroll
+    for (int r = 0; r < 6; r++) ST(s.pid, r, pd[r]);
+  }
+  if (on_vel) {
+#pragma unroll
+    for (int r = 6; r < 12; r++) ST(s.pid, r, pd[r]);
+  }
+  if (on_att) {
+#pragma unroll
+    for (int r = 12; r < 18; r++) ST(s.pid, r, pd[r]);
+  }
+  if (on_rate) {
+#pragma unroll
+    for (int r = 18; r < 24; r++) ST(s.pid, r, pd[r]);
+  }
+  ST(s.imu, 0, imu.x);
+  ST(s.imu, 1, imu.y);
+  ST(s.imu, 2, imu.z);
+  const uint32_t new_flags = flags & ~FLAG_VPREV;
+  if (new_flags != s.flags[i]) s.flags[i] = new_flags;
+  // packed position for the collision pass / the cross-shard all-gather
+  double* gp = s.gpos + 3 * (s.shard_begin + i);
+  gp[0]      = x.x;
+  gp[1]      = x.y;
+  gp[2]      = x.z;
+#undef LD
+#undef ST
+}
+
+__global__ void publish_positions_kernel(DevState s) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= s.n) return;
+  double* gp = s.gpos + 3 * (s.shard_begin + i);
+  gp[0]      = s.st[0 * s.ld + i];
+  gp[1]      = s.st[1 * s.ld + i];
+  gp[2]      = s.st[2 * s.ld + i];
+}
+
+template <int NM_T, int MODE_T>
+void launch_one(const DevState& s, double dt, int k, int any_moment, cudaStream_t st) {
+  const int      threads = 128;
+  const unsigned blocks  = unsigned((s.n + threads - 1) / threads);
+  uav_step_kernel<NM_T, MODE_T><<<blocks, threads, 0, st>>>(s, dt, k, any_moment);
+}
+
+template <int NM_T>
+void launch_nm(const DevState& s, double dt, int k, int mode, int any_moment, cudaStream_t st) {
+  switch (mode) {
+    case MRSB_ACTUATOR_CMD:
+      launch_one<NM_T, MRSB_ACTUATOR_CMD>(s, dt, k, any_moment, st);
+      break;
+    case MRSB_VELOCITY_HDG_RATE_CMD:
+      launch_one<NM_T, MRSB_VELOCITY_HDG_RATE_CMD>(s, dt, k, any_moment, st);
+      break;
+    case MRSB_VELOCITY_HDG_CMD:
+      launch_one<NM_T, MRSB_VELOCITY_HDG_CMD>(s, dt, k, any_moment, st);
+      break;
+    case MRSB_POSITION_CMD:
+      launch_one<NM_T, MRSB_POSITION_CMD>(s, dt, k, any_moment, st);
+      break;
+    default:
+      launch_one<NM_T, -1>(s, dt, k, any_moment, st);
+      break;
+  }
+}
+
+}  // namespace
+
+int launch_step(const DevState& s, double dt, int k_substeps, int uniform_mode, int uniform_nm, bool any_moment, cudaStream_t stream) {
+  if (s.n <= 0) return 0;
+  switch (uniform_nm) {
+    case 4:
+      launch_nm<4>(s, dt, k_substeps, uniform_mode, any_moment, stream);
+      break;
+    case 6:
+      launch_nm<6>(s, dt, k_substeps, uniform_mode, any_moment, stream);
+      break;
+    case 8:
+      launch_nm<8>(s, dt, k_substeps, uniform_mode, any_moment, stream);
+      break;
+    default:
+      launch_nm<0>(s, dt, k_substeps, uniform_mode, any_moment, stream);
+      break;
+  }
+  return 1;
+}
+
+int launch_publish_positions(const DevState& s, cudaStream_t stream) {
+  if (s.n <= 0) return 0;
+  publish_positions_kernel<<<unsigned((s.n + 255) / 256), 256, 0, stream>>>(s);
+  return 1;
+}
