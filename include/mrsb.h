@@ -243,6 +243,10 @@ int mrsb_handle_collisions(mrsb_handle h);
  * sorted by (i, j).  ij holds up to cap pairs (2*cap int32).  *count receives the number found
  * (may exceed cap -> MRSB_ERR_CAPACITY). */
 int mrsb_get_collision_pairs(mrsb_handle h, int32_t* ij, int64_t cap, int64_t* count);
+/* Size of the device-side pair buffer (default max(4096, 4*n_local) pairs).  A pass that finds more
+ * still applies every force / crash flag; only the recorded list is truncated and
+ * mrsb_get_collision_pairs then reports MRSB_ERR_CAPACITY with the true count. */
+int mrsb_set_pair_capacity(mrsb_handle h, int64_t max_pairs);
 /* Cumulative counters since create: [0] steps, [1] collision passes, [2] directed pairs emitted
  * by the last pass, [3] crashed UAVs in this shard, [4] kernels launched by this handle. */
 int mrsb_get_counters(mrsb_handle h, int64_t* out5);

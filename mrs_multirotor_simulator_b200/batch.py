@@ -263,6 +263,9 @@ class UavBatch:
             check(self._L.mrsb_get_collision_pairs(self.h, _ptr(pairs), k, C.byref(cnt)))
         return pairs[:k]
 
+    def set_pair_capacity(self, max_pairs):
+        check(self._L.mrsb_set_pair_capacity(self.h, int(max_pairs)))
+
     def counters(self):
         out = np.zeros(5, dtype=np.int64)
         check(self._L.mrsb_get_counters(self.h, _ptr(out)))

@@ -923,6 +923,19 @@ int mrsb_get_collision_pairs(mrsb_handle h, int32_t* ij, int64_t cap, int64_t* c
   return MRSB_OK;
 }
 
+int mrsb_set_pair_capacity(mrsb_handle h, int64_t max_pairs) {
+  GUARD(h);
+  if (max_pairs < 1) return fail(MRSB_ERR_INVALID, "max_pairs must be >= 1");
+  CU(cudaStreamSynchronize(h->stream));
+  int32_t* fresh = nullptr;
+  CU(cudaMalloc(&fresh, sizeof(int32_t) * 2 * size_t(max_pairs)));
+  if (h->grid.pairs) CU(cudaFree(h->grid.pairs));
+  h->grid.pairs    = fresh;
+  h->grid.pair_cap = max_pairs;
+  CU(cudaMemsetAsync(h->grid.counters, 0, sizeof(unsigned long long), h->stream));
+  return MRSB_OK;
+}
+
 int mrsb_get_counters(mrsb_handle h, int64_t* out5) {
   GUARD(h);
   unsigned long long found = 0;

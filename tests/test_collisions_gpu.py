@@ -35,11 +35,13 @@ def geometry(types, tou):
     return arm, prop, mass
 
 
-def run_gpu_pass(types, tou, xyz, crash, rebounce):
+def run_gpu_pass(types, tou, xyz, crash, rebounce, pair_cap=None):
     from mrs_multirotor_simulator_b200 import UavBatch
 
     n = len(xyz)
     b = UavBatch(types, type_of_uav=tou, spawn_xyz=xyz, n=n)
+    if pair_cap:
+        b.set_pair_capacity(pair_cap)
     b.set_collisions(True, crash, rebounce)
     b.handle_collisions()
     return b, b.get_collision_pairs(), b.get_force(), b.has_crashed()
@@ -90,9 +92,9 @@ def test_dense_cluster_many_neighbours():
     xyz = np.stack([rand(5, 0, n, -0.6, 0.6), rand(5, 1, n, -0.6, 0.6), rand(5, 2, n, 9.4, 10.6)], axis=1)
     xyz[10] = xyz[11]  # coincident distinct UAVs collide with zero force (normalized(0) = 0)
     arm, prop, mass = geometry(types, tou)
-    ref_pairs, ref_forces, _ = O.collide_snapshot(xyz, arm, prop, mass, False, 100.0, engine=ENGINE)
-    port_pairs, port_forces, _ = O.collide_snapshot(xyz, arm, prop, mass, False, 100.0, engine="port")
-    b, pairs, forces, _ = run_gpu_pass(types, tou, xyz, False, 100.0)
+    ref_pairs, ref_forces, _ = O.collide_snapshot(xyz, arm, prop, mass, False, 100.0, engine=ENGINE, cap=n * n)
+    port_pairs, port_forces, _ = O.collide_snapshot(xyz, arm, prop, mass, False, 100.0, engine="port", cap=n * n)
+    b, pairs, forces, _ = run_gpu_pass(types, tou, xyz, False, 100.0, pair_cap=n * n)
     assert len(ref_pairs) > 10 * n
     assert np.array_equal(sorted_pairs(ref_pairs), pairs)
     assert np.array_equal(port_forces, forces)  # same summation order as the port: bit exact

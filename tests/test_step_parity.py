@@ -188,7 +188,7 @@ def test_ground_and_takeoff_patch():
     assert gpu.get_params(1).takeoff_patch_enabled == 0 and orc.get_params(1).takeoff_patch_enabled == 0
     # land on the ground again
     cmd = np.tile([0.0, 0.0, -1.5, 0.0], (n, 1))
-    orc.set_input(O.VELOCITY_HDG_RATE_CMD, cmd, idx=np.arange(0, n, 2))
+    orc.set_input(O.VELOCITY_HDG_RATE_CMD, cmd[0::2], idx=np.arange(0, n, 2))
     gpu.set_input(O.VELOCITY_HDG_RATE_CMD, cmd[0::2], idx=np.arange(0, n, 2))
     orc.make_step(0.01, 800)
     for _ in range(800):
