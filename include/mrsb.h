@@ -276,6 +276,12 @@ typedef struct mrsb_device_view {
 } mrsb_device_view;
 int mrsb_get_device_view(mrsb_handle h, mrsb_device_view* out);
 
+/* ---- roofline denominators, measured on `device` (used by bench.py) --------------------------
+ * FP64 FMA throughput in TFLOP/s (2 flop per FMA) and device-to-device copy bandwidth in GB/s
+ * (read + write bytes). */
+int mrsb_microbench_fp64(int device, double* tflops);
+int mrsb_microbench_copy(int device, double* gbs);
+
 #ifdef __cplusplus
 }
 #endif

@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmrsb.so")
+LIB_PATH = os.environ.get("MRSB_LIB_PATH") or os.path.join(HERE, "libmrsb.so")  # MRSB_LIB_PATH: kernel-variant experiments only
 MAX_MOTORS = 8
 
 i32p = C.POINTER(C.c_int32)
@@ -109,6 +109,8 @@ SIGNATURES = {
     "mrsb_publish_positions": (C.c_int, [H]),
     "mrsb_handle_collisions_gathered": (C.c_int, [H]),
     "mrsb_get_device_view": (C.c_int, [H, C.POINTER(DeviceView)]),
+    "mrsb_microbench_fp64": (C.c_int, [C.c_int, C.POINTER(C.c_double)]),
+    "mrsb_microbench_copy": (C.c_int, [C.c_int, C.POINTER(C.c_double)]),
 }
 
 _lib = None

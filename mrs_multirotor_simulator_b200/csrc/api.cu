@@ -303,7 +303,7 @@ int mrsb_destroy(mrsb_handle h) {
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   void* ptrs[] = {h->ds.st,     h->ds.vprev,  h->ds.rpm,      h->ds.pid,      h->ds.fext,         h->ds.mext,       h->ds.imu,    h->ds.initz,
                   h->ds.cmd,    h->ds.ff,     h->ds.flags,    h->ds.mode,     h->ds.gpos,         h->d_params,      h->d_pset,    h->d_stage,
-                  h->d_idx,     h->grid.keys, h->grid.keys_sorted, h->grid.vals, h->grid.vals_sorted, h->grid.begin, h->grid.rec, h->grid.pairs,
+                  h->d_idx,     h->grid.bucket, h->grid.rank, h->grid.count, h->grid.aabb, h->grid.begin, h->grid.rec, h->grid.pairs,
                   h->grid.counters, h->cub_tmp};
   for (void* p : ptrs)
     if (p) cudaFree(p);
@@ -422,16 +422,16 @@ int mrsb_create(const mrsb_create_info* info, mrsb_handle* out) {
     while ((size_t(1) << bits) < 2 * ng && bits < 30) bits++;
     g.bits      = bits;
     g.n_buckets = 1u << bits;
-    CREATE_RC(dalloc(&g.keys, ng));
-    CREATE_RC(dalloc(&g.keys_sorted, ng));
-    CREATE_RC(dalloc(&g.vals, ng));
-    CREATE_RC(dalloc(&g.vals_sorted, ng));
+    CREATE_RC(dalloc(&g.bucket, ng));
+    CREATE_RC(dalloc(&g.rank, ng));
+    CREATE_RC(dalloc(&g.count, size_t(g.n_buckets) + 1));
     CREATE_RC(dalloc(&g.begin, size_t(g.n_buckets) + 1));
+    CREATE_RC(dalloc(&g.aabb, 6));
     CREATE_RC(dalloc(&g.rec, ng));
     g.pair_cap = int64_t(std::max<size_t>(4096, 4 * size_t(std::max<int64_t>(s.n, 1))));
     CREATE_RC(dalloc(&g.pairs, 2 * size_t(g.pair_cap)));
     CREATE_RC(dalloc(&g.counters, 4));
-    h->cub_tmp_bytes = collide_tmp_bytes(s.n_global);
+    h->cub_tmp_bytes = collide_tmp_bytes(int64_t(g.n_buckets) + 1);
     CREATE_CU(cudaMalloc(&h->cub_tmp, std::max<size_t>(h->cub_tmp_bytes, 16)));
   }
   h->shard_begin_of = {s.shard_begin};

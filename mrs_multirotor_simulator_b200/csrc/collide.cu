@@ -1,32 +1,37 @@
 // collide.cu — K2/K3: MultirotorSimulator::handleCollisions (SIM:295-359) as a uniform-grid spatial
-// hash over the packed positions of the WHOLE swarm (after the cross-shard all-gather), queried for
-// this shard's UAVs only.
+// hash over the packed positions of the swarm (after the cross-shard all-gather), queried for this
+// shard's UAVs only.
 //
 // The reference rebuilds a nanoflann KD-tree every tick and runs one radius query per UAV with
-// squared "radius" 3.0 (SIM:309-328).  Here:
-//   K2a  hash:     cell = floor(p / 2 m) (2 m > sqrt(3) so the 3x3x3 stencil is a superset of the
-//                  search ball); bucket = (mix(cy,cz) + cx) mod B, B = 2^bits >= 2N.  Cells adjacent
-//                  in x land in adjacent buckets, so one stencil row is ONE contiguous range.
-//   K2b  sort:     CUB radix sort of (bucket, index) on `bits` bits (stable: equal buckets stay in
-//                  ascending index order -> deterministic traversal).
-//   K2c  ranges:   begin[b] = first sorted slot with bucket >= b (gap-filling scan of the sorted keys).
-//   K2d  records:  rec[slot] = {x, y, z, index} gathered in sorted order (32-byte records: a
-//                  candidate costs exactly one DRAM sector).
-//   K3   collide:  one thread per sorted slot; 9 range probes; per candidate the EXACT reference
-//                  predicate, evaluated with explicit round-to-nearest multiplies and adds (no FMA
-//                  contraction) in nanoflann's order  d2 = ((dx*dx) + dy*dy) + dz*dz, dx = q - p
-//                  (NF:479-484), accepted iff d2 < 3.0 (NF:305-309, strict) and j != i (SIM:335)
-//                  and d2 < ((arm_i+prop_i)+arm_j)+prop_j (SIM:342,346: squared metres against
-//                  metres — reproduced as is).
-// Bucket aliasing (two cells sharing a bucket) only adds candidates; a candidate is accepted in the
-// one probe whose (cy,cz) row matches its own cell, so nothing is counted twice.
+// squared "radius" 3.0 (SIM:309-328).  Here, per pass:
+//   K2a  box      (sharded runs only) bounding box of this shard's positions; a remote UAV further
+//                 than 2 m (> sqrt 3) outside it cannot be a neighbour of any local UAV and is not
+//                 inserted, so the table holds n_local + halo entries instead of n_global.
+//   K2b  count    cell = floor(p / 4 m); bucket = (mix(cy,cz) + cx) mod B, B = 2^bits >= 2 n_global;
+//                 rank = atomicAdd(count[bucket], 1).  Cells adjacent in x land in adjacent buckets,
+//                 so one stencil row is ONE contiguous range of the grouped records.
+//   K2c  scan     begin = exclusive prefix sum of count (CUB DeviceScan).
+//   K2d  scatter  rec[begin[bucket] + rank] = {x, y, z, index}  (32-byte records: a candidate costs
+//                 exactly one DRAM sector).  This is a counting sort: no radix passes.
+//   K3   collide  one thread per record; the search ball of radius sqrt(3) < 2 m around p touches at
+//                 most 2 cells per axis (interval [p-2, p+2] has the length of one 4 m cell), i.e.
+//                 <= 4 stencil rows (cy0..cy1 x cz0..cz1), each one contiguous range cx0..cx1; per
+//                 candidate the EXACT reference predicate, evaluated with explicit round-to-nearest
+//                 multiplies and adds (no FMA contraction) in nanoflann's order
+//                 d2 = ((dx*dx) + dy*dy) + dz*dz, dx = q - p (NF:479-484), accepted iff d2 < 3.0
+//                 (NF:305-309, strict) and j != i (SIM:335) and
+//                 d2 < ((arm_i+prop_i)+arm_j)+prop_j (SIM:342,346: squared metres against metres —
+//                 reproduced as is).
+// Bucket aliasing (two cells sharing a bucket) only adds candidates, which fail d2 < 3.0 unless they
+// are true neighbours; a true neighbour is accepted only in the probe whose (cy,cz) row is its own
+// cell row, so nothing is counted twice.  The arrival order inside a bucket is not deterministic;
+// results are: pair lists are sorted on retrieval, and force sums of >= 3 terms are re-accumulated
+// in ascending j (sums of <= 2 terms are order-independent bit for bit).
 //
 // Crash mode (SIM:347-348) marks the NEIGHBOUR crashed.  A shard must not write remote state, so the
 // owner of i evaluates the mirrored test d2 < ((arm_j+prop_j)+arm_i)+prop_i — the exact threshold
-// the owner of j uses for the directed pair (j,i) — and marks i itself.  Rebounce mode (SIM:350)
-// accumulates F_i in ascending j (the reference's KD-tree order is not reproducible without the
-// tree; sums of <= 2 terms are order-independent bit for bit, longer ones agree to rounding).
-#include <cub/device/device_radix_sort.cuh>
+// the owner of j uses for the directed pair (j,i) — and marks i itself.
+#include <cub/device/device_scan.cuh>
 
 #include "internal.h"
 
@@ -34,9 +39,12 @@ namespace {
 
 #define DEV __device__ __forceinline__
 
+constexpr double kInvCell = 0.25;  // 4 m cells
+constexpr double kReach   = 2.0;   // > sqrt(3.0), exactly representable
+
 DEV int cell_of(double v) {
-  // floor(v/2) saturated to +-2^29 (NaN -> 0); x*0.5 is exact
-  double c = floor(v * 0.5);
+  // floor(v / 4 m) saturated to +-2^29 (NaN -> 0); v * 0.25 is exact
+  double c = floor(v * kInvCell);
   c        = fmin(fmax(c, -536870912.0), 536870912.0);
   return (c == c) ? int(c) : 0;
 }
@@ -49,30 +57,78 @@ DEV uint32_t row_hash(int cy, int cz) {
   return h;
 }
 
-__global__ void hash_kernel(const double* __restrict__ gpos, int64_t n, uint32_t mask, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+// order-preserving map double -> uint64 (for atomicMin / atomicMax)
+DEV unsigned long long enc(double v) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+DEV double dec(unsigned long long e) {
+  const unsigned long long b = (e >> 63) ? (e & 0x7fffffffffffffffull) : ~e;
+  return __longlong_as_double((long long)b);
+}
+
+__global__ void box_reset_kernel(unsigned long long* aabb) {
+  if (threadIdx.x < 3) aabb[threadIdx.x] = ~0ull;
+  if (threadIdx.x >= 3 && threadIdx.x < 6) aabb[threadIdx.x] = 0ull;
+}
+
+__global__ void __launch_bounds__(256) box_kernel(const double* __restrict__ gpos, int64_t begin, int64_t n, unsigned long long* aabb) {
+  unsigned long long lo[3] = {~0ull, ~0ull, ~0ull}, hi[3] = {0ull, 0ull, 0ull};
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+    const double* p = gpos + 3 * (begin + i);
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      const unsigned long long e = enc(p[c]);
+      lo[c]                      = min(lo[c], e);
+      hi[c]                      = max(hi[c], e);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    for (int o = 16; o > 0; o >>= 1) {
+      lo[c] = min(lo[c], __shfl_xor_sync(0xffffffffu, lo[c], o));
+      hi[c] = max(hi[c], __shfl_xor_sync(0xffffffffu, hi[c], o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+      atomicMin(&aabb[c], lo[c]);
+      atomicMax(&aabb[3 + c], hi[c]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) count_kernel(const double* __restrict__ gpos, int64_t n, int64_t shard_begin, int64_t n_local, int filter,
+                                                    const unsigned long long* __restrict__ aabb, uint32_t mask, uint32_t* __restrict__ count,
+                                                    uint32_t* __restrict__ bucket, uint32_t* __restrict__ rank) {
   const int64_t j = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (j >= n) return;
-  const double* p  = gpos + 3 * j;
-  const int     cx = cell_of(p[0]), cy = cell_of(p[1]), cz = cell_of(p[2]);
-  keys[j]          = (row_hash(cy, cz) + uint32_t(cx)) & mask;
-  vals[j]          = uint32_t(j);
+  const double* p = gpos + 3 * j;
+  const double  x = p[0], y = p[1], z = p[2];
+  if (filter) {
+    const int64_t l = j - shard_begin;
+    if (l < 0 || l >= n_local) {
+      // remote: keep it only if it can reach this shard's box (NaN compares false -> kept)
+      const bool out = x < dec(aabb[0]) - kReach || y < dec(aabb[1]) - kReach || z < dec(aabb[2]) - kReach || x > dec(aabb[3]) + kReach ||
+                       y > dec(aabb[4]) + kReach || z > dec(aabb[5]) + kReach;
+      if (out) {
+        bucket[j] = 0xFFFFFFFFu;
+        return;
+      }
+    }
+  }
+  const uint32_t b = (row_hash(cell_of(y), cell_of(z)) + uint32_t(cell_of(x))) & mask;
+  bucket[j]        = b;
+  rank[j]          = atomicAdd(&count[b], 1u);
 }
 
-// begin[b] = first slot whose key >= b ; begin[n_buckets] = n
-__global__ void ranges_kernel(const uint32_t* __restrict__ keys_sorted, int64_t n, uint32_t n_buckets, uint32_t* __restrict__ begin) {
-  const int64_t p = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (p > n) return;
-  const uint32_t hi = (p == n) ? n_buckets : keys_sorted[p];
-  const int64_t  lo = (p == 0) ? -1 : int64_t(keys_sorted[p - 1]);
-  for (int64_t b = lo + 1; b <= int64_t(hi); b++) begin[b] = uint32_t(p);
-}
-
-__global__ void records_kernel(const double* __restrict__ gpos, const uint32_t* __restrict__ vals_sorted, int64_t n, double4* __restrict__ rec) {
-  const int64_t p = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (p >= n) return;
-  const uint32_t j = vals_sorted[p];
-  const double*  q = gpos + 3 * int64_t(j);
-  rec[p]           = make_double4(q[0], q[1], q[2], __longlong_as_double((long long)j));
+__global__ void __launch_bounds__(256) scatter_kernel(const double* __restrict__ gpos, int64_t n, const uint32_t* __restrict__ bucket,
+                                                      const uint32_t* __restrict__ rank, const uint32_t* __restrict__ begin,
+                                                      double4* __restrict__ rec) {
+  const int64_t j = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const uint32_t b = bucket[j];
+  if (b == 0xFFFFFFFFu) return;
+  const double* q = gpos + 3 * j;
+  rec[begin[b] + rank[j]] = make_double4(q[0], q[1], q[2], __longlong_as_double((long long)j));
 }
 
 // nanoflann L2 metric for dim 3, no contraction
@@ -84,58 +140,59 @@ DEV double nf_dist2(double ax, double ay, double az, double bx, double by, doubl
   return r;
 }
 
-struct Hit {
-  int    count;
-  double fx, fy, fz;
+struct Probe {
+  uint32_t lo, hi;  // record range
+  int      cy, cz;  // the stencil row this probe stands for
 };
 
-// Visit every neighbour j of UAV i (record q) that passes the reference predicate.
-//   only_above: visit only j > after (ordered re-scan); returns the smallest such j in *next.
-template <class F>
-DEV void for_each_candidate(const DevGrid& g, const double4 q, int cx, int cy, int cz, F f) {
+// the <= 4 stencil rows around q, each one contiguous record range cx0..cx1 (two ranges in the 1-in-B case of a table wrap)
+DEV int make_probes(const DevGrid& g, const double4& q, Probe pr[8]) {
   const uint32_t mask = g.n_buckets - 1;
-#pragma unroll 1
-  for (int dz = -1; dz <= 1; dz++) {
-#pragma unroll 1
-    for (int dy = -1; dy <= 1; dy++) {
-      const uint32_t b1 = (row_hash(cy + dy, cz + dz) + uint32_t(cx)) & mask;
-      uint32_t       lo, hi;
-      if (b1 >= 1 && b1 + 1 <= mask) {
-        lo = g.begin[b1 - 1];
-        hi = g.begin[b1 + 2];
-        for (uint32_t p = lo; p < hi; p++) {
-          const double4 r = g.rec[p];
-          if (cell_of(r.y) == cy + dy && cell_of(r.z) == cz + dz && abs(cell_of(r.x) - cx) <= 1) f(r);
-        }
-      } else {  // stencil row wraps around the bucket table: probe the three buckets one by one
-        for (int dx = -1; dx <= 1; dx++) {
-          const uint32_t b = (b1 + uint32_t(dx)) & mask;
-          lo               = g.begin[b];
-          hi               = g.begin[b + 1];
-          for (uint32_t p = lo; p < hi; p++) {
-            const double4 r = g.rec[p];
-            if (cell_of(r.y) == cy + dy && cell_of(r.z) == cz + dz && cell_of(r.x) == cx + dx) f(r);
-          }
-        }
+  const int      cx0 = cell_of(q.x - kReach), cx1 = cell_of(q.x + kReach);
+  const int      cy0 = cell_of(q.y - kReach), cy1 = cell_of(q.y + kReach);
+  const int      cz0 = cell_of(q.z - kReach), cz1 = cell_of(q.z + kReach);
+  int            n   = 0;
+  for (int cz = cz0; cz <= cz1; cz++) {
+    for (int cy = cy0; cy <= cy1; cy++) {
+      const uint32_t b0 = (row_hash(cy, cz) + uint32_t(cx0)) & mask;
+      const uint32_t w  = uint32_t(cx1 - cx0);  // 0 or 1
+      pr[n].cy          = cy;
+      pr[n].cz          = cz;
+      if (b0 + w <= mask) {
+        pr[n].lo = g.begin[b0];
+        pr[n].hi = g.begin[b0 + w + 1];
+        n++;
+      } else {  // the two x cells straddle the end of the bucket table: two ranges for this row
+        pr[n].lo = g.begin[b0];
+        pr[n].hi = g.begin[b0 + 1];
+        n++;
+        pr[n].cy = cy;
+        pr[n].cz = cz;
+        pr[n].lo = g.begin[0];
+        pr[n].hi = g.begin[1];
+        n++;
       }
     }
   }
+  return n;
 }
 
 __global__ void __launch_bounds__(128) collide_kernel(DevState s, DevGrid g, int crash_mode, double rebounce) {
   const int64_t p = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (p >= s.n_global) return;
+  if (p >= int64_t(g.begin[g.n_buckets])) return;
   const double4 q  = g.rec[p];
   const int64_t gi = __double_as_longlong(q.w);
   const int64_t li = gi - s.shard_begin;
-  if (li < 0 || li >= s.n) return;  // not ours: its owner handles it
+  if (li < 0 || li >= s.n) return;  // halo record: its owner handles it
 
-  const int cx = cell_of(q.x), cy = cell_of(q.y), cz = cell_of(q.z);
   const DevParams* __restrict__ Pi = s.params + s.pset[gi];
   const double ai = Pi->arm_length, pi_ = Pi->prop_radius, mi = Pi->mass;
   const double api = __dadd_rn(ai, pi_);
 
-  int    hits = 0;
+  Probe     pr[8];
+  const int n_probes = make_probes(g, q, pr);
+
+  int    hits       = 0;
   bool   crashed_me = false;
   double fx = 0.0, fy = 0.0, fz = 0.0;
 
@@ -157,54 +214,66 @@ __global__ void __launch_bounds__(128) collide_kernel(DevState s, DevGrid g, int
     cz_             = __dmul_rn(__dmul_rn(__dmul_rn(rebounce, nz), mi), wt);
   };
 
-  for_each_candidate(g, q, cx, cy, cz, [&](const double4& r) {
-    const int64_t gj = __double_as_longlong(r.w);
-    if (gj == gi) return;  // SIM:335
-    const double d2 = nf_dist2(q.x, q.y, q.z, r.x, r.y, r.z);
-    if (!(d2 < 3.0)) return;  // NF:305-309
-    const DevParams* __restrict__ Pj = s.params + s.pset[gj];
-    const double aj = Pj->arm_length, pj = Pj->prop_radius;
-    const double crit_ij = __dadd_rn(__dadd_rn(api, aj), pj);  // SIM:342
-    if (d2 < crit_ij) {                                         // SIM:346
-      hits++;
-      const unsigned long long slot = atomicAdd(g.counters, 1ull);
-      if (slot < (unsigned long long)g.pair_cap) {
-        g.pairs[2 * slot]     = int32_t(gi);
-        g.pairs[2 * slot + 1] = int32_t(gj);
+  // a record r found in probe k is a genuine, not-yet-seen neighbour candidate iff it lies in the
+  // search ball AND its own cell row is the probe's row (rejects bucket aliases and duplicates)
+  auto in_ball = [&](const double4& r, const Probe& k, double& d2) {
+    d2 = nf_dist2(q.x, q.y, q.z, r.x, r.y, r.z);
+    if (!(d2 < 3.0)) return false;  // NF:305-309
+    return cell_of(r.y) == k.cy && cell_of(r.z) == k.cz;
+  };
+
+  for (int k = 0; k < n_probes; k++) {
+    for (uint32_t t = pr[k].lo; t < pr[k].hi; t++) {
+      const double4 r  = g.rec[t];
+      const int64_t gj = __double_as_longlong(r.w);
+      double        d2;
+      if (gj == gi || !in_ball(r, pr[k], d2)) continue;  // SIM:335
+      const DevParams* __restrict__ Pj = s.params + s.pset[gj];
+      const double aj = Pj->arm_length, pj = Pj->prop_radius;
+      const double crit_ij = __dadd_rn(__dadd_rn(api, aj), pj);  // SIM:342
+      if (d2 < crit_ij) {                                         // SIM:346
+        hits++;
+        const unsigned long long slot = atomicAdd(g.counters, 1ull);
+        if (slot < (unsigned long long)g.pair_cap) {
+          g.pairs[2 * slot]     = int32_t(gi);
+          g.pairs[2 * slot + 1] = int32_t(gj);
+        }
+        if (!crash_mode) {
+          double ax, ay, az;
+          contribution(r, Pj, ax, ay, az);
+          fx = __dadd_rn(fx, ax);
+          fy = __dadd_rn(fy, ay);
+          fz = __dadd_rn(fz, az);
+        }
       }
-      if (!crash_mode) {
-        double ax, ay, az;
-        contribution(r, Pj, ax, ay, az);
-        fx = __dadd_rn(fx, ax);
-        fy = __dadd_rn(fy, ay);
-        fz = __dadd_rn(fz, az);
+      if (crash_mode) {
+        const double crit_ji = __dadd_rn(__dadd_rn(__dadd_rn(aj, pj), ai), pi_);  // threshold of the directed pair (j,i)
+        if (d2 < crit_ji) crashed_me = true;
       }
     }
-    if (crash_mode) {
-      const double crit_ji = __dadd_rn(__dadd_rn(__dadd_rn(aj, pj), ai), pi_);  // threshold of the directed pair (j,i)
-      if (d2 < crit_ji) crashed_me = true;
-    }
-  });
+  }
 
   if (!crash_mode && hits >= 3) {
-    // >= 3 simultaneous neighbours: redo the sum in ascending j so the result does not depend on
-    // bucket order (selection by repeated scan; such clusters are rare and small)
-    fx = fy = fz   = 0.0;
-    int64_t last   = -1;
-    for (int k = 0; k < hits; k++) {
+    // >= 3 simultaneous neighbours: redo the sum in ascending j so that the result does not depend
+    // on the arrival order inside the buckets (selection by repeated scan; such clusters are rare)
+    fx = fy = fz = 0.0;
+    int64_t last = -1;
+    for (int c = 0; c < hits; c++) {
       int64_t best = INT64_MAX;
       double  bx = 0, by = 0, bz = 0;
-      for_each_candidate(g, q, cx, cy, cz, [&](const double4& r) {
-        const int64_t gj = __double_as_longlong(r.w);
-        if (gj == gi || gj <= last || gj >= best) return;
-        const double d2 = nf_dist2(q.x, q.y, q.z, r.x, r.y, r.z);
-        if (!(d2 < 3.0)) return;
-        const DevParams* __restrict__ Pj = s.params + s.pset[gj];
-        if (d2 < __dadd_rn(__dadd_rn(api, Pj->arm_length), Pj->prop_radius)) {
-          best = gj;
-          contribution(r, Pj, bx, by, bz);
+      for (int k = 0; k < n_probes; k++) {
+        for (uint32_t t = pr[k].lo; t < pr[k].hi; t++) {
+          const double4 r  = g.rec[t];
+          const int64_t gj = __double_as_longlong(r.w);
+          double        d2;
+          if (gj == gi || gj <= last || gj >= best || !in_ball(r, pr[k], d2)) continue;
+          const DevParams* __restrict__ Pj = s.params + s.pset[gj];
+          if (d2 < __dadd_rn(__dadd_rn(api, Pj->arm_length), Pj->prop_radius)) {
+            best = gj;
+            contribution(r, Pj, bx, by, bz);
+          }
         }
-      });
+      }
       if (best == INT64_MAX) break;
       fx   = __dadd_rn(fx, bx);
       fy   = __dadd_rn(fy, by);
@@ -222,23 +291,29 @@ __global__ void __launch_bounds__(128) collide_kernel(DevState s, DevGrid g, int
 
 }  // namespace
 
-size_t collide_tmp_bytes(int64_t n_global) {
+size_t collide_tmp_bytes(int64_t n_items) {
   size_t bytes = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const uint32_t*)nullptr, (uint32_t*)nullptr,
-                                  int(n_global), 0, 32);
+  cub::DeviceScan::ExclusiveSum(nullptr, bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, int(n_items));
   return bytes;
 }
 
 int launch_collide(const DevState& s, const DevGrid& g, int crash_mode, double rebounce, void* cub_tmp, size_t cub_tmp_bytes, cudaStream_t stream) {
   const int64_t n = s.n_global;
   if (n <= 0) return 0;
-  const int      T  = 256;
-  const unsigned nb = unsigned((n + T - 1) / T);
+  const int      T      = 256;
+  const unsigned nb     = unsigned((n + T - 1) / T);
+  const int      filter = s.n_global > s.n;
+  int            own    = 0;
   cudaMemsetAsync(g.counters, 0, sizeof(unsigned long long), stream);
-  hash_kernel<<<nb, T, 0, stream>>>(s.gpos, n, g.n_buckets - 1, g.keys, g.vals);
-  cub::DeviceRadixSort::SortPairs(cub_tmp, cub_tmp_bytes, g.keys, g.keys_sorted, g.vals, g.vals_sorted, int(n), 0, int(g.bits), stream);
-  ranges_kernel<<<unsigned((n + 1 + T - 1) / T), T, 0, stream>>>(g.keys_sorted, n, g.n_buckets, g.begin);
-  records_kernel<<<nb, T, 0, stream>>>(s.gpos, g.vals_sorted, n, g.rec);
+  cudaMemsetAsync(g.count, 0, sizeof(uint32_t) * (size_t(g.n_buckets) + 1), stream);
+  if (filter) {
+    box_reset_kernel<<<1, 32, 0, stream>>>(g.aabb);
+    if (s.n > 0) box_kernel<<<unsigned(std::min<int64_t>((s.n + T - 1) / T, 296)), T, 0, stream>>>(s.gpos, s.shard_begin, s.n, g.aabb);
+    own += 2;
+  }
+  count_kernel<<<nb, T, 0, stream>>>(s.gpos, n, s.shard_begin, s.n, filter, g.aabb, g.n_buckets - 1, g.count, g.bucket, g.rank);
+  cub::DeviceScan::ExclusiveSum(cub_tmp, cub_tmp_bytes, g.count, g.begin, int(g.n_buckets) + 1, stream);
+  scatter_kernel<<<nb, T, 0, stream>>>(s.gpos, n, g.bucket, g.rank, g.begin, g.rec);
   collide_kernel<<<unsigned((n + 127) / 128), 128, 0, stream>>>(s, g, crash_mode, rebounce);
-  return 6;  // hash + (>=1) sort + ranges + records + collide (+ memset); sort passes counted as one
+  return own + 3;  // own kernels: [box_reset, box,] count, scatter, collide (CUB's scan kernels and the memsets are not counted)
 }

@@ -79,14 +79,14 @@ struct DevState {
 
 // collision pass workspace
 struct DevGrid {
-  uint32_t  n_buckets;  // power of two
+  uint32_t  n_buckets;  // power of two >= 2 * n_global
   uint32_t  bits;
-  uint32_t* keys;       // [n_global] bucket of each UAV
-  uint32_t* keys_sorted;
-  uint32_t* vals;       // [n_global] iota
-  uint32_t* vals_sorted;
-  uint32_t* begin;      // [n_buckets+1] first sorted slot of each bucket
-  double4*  rec;        // [n_global] sorted records {x,y,z, index bits}
+  uint32_t* bucket;     // [n_global] bucket of each UAV, 0xFFFFFFFF = not inserted (remote and outside this shard's box)
+  uint32_t* rank;       // [n_global] arrival rank inside its bucket
+  uint32_t* count;      // [n_buckets+1] occupancy histogram (last entry stays 0)
+  uint32_t* begin;      // [n_buckets+1] exclusive scan of count; begin[n_buckets] = number of inserted UAVs
+  double4*  rec;        // [n_global] records {x,y,z, index bits} grouped by bucket
+  unsigned long long* aabb;  // [6] order-preserving encoding of min xyz / max xyz of this shard's positions
   int32_t*  pairs;      // [pair_cap][2]
   int64_t   pair_cap;
   unsigned long long* counters;  // [0] pairs found by the last pass

@@ -156,8 +156,19 @@ DEV Vec3 attitude_error(const Rot& Rd, const Rot& R) {
   return mk((a12 - a21) * 0.5, (a20 - a02) * 0.5, (a01 - a10) * 0.5);
 }
 
-template <int NM_T, int MODE_T>
-__global__ void __launch_bounds__(128) uav_step_kernel(DevState s, double dt, int k_sub, int any_moment) {
+#ifndef MRSB_STEP_THREADS
+#define MRSB_STEP_THREADS 128
+#endif
+#ifndef MRSB_STEP_MINB
+#define MRSB_STEP_MINB 2
+#endif
+
+// NM_T: motors per UAV if uniform over the batch (4/6/8), 0 = read per UAV.  MODE_T: INPUT_MODE if
+// uniform, -1 = read per UAV.  ONE: k_sub == 1 (no substep loop: PID state, commands and motor
+// speeds are dead after their single use, which is worth ~60 registers).
+template <int NM_T, int MODE_T, bool ONE>
+__global__ void __launch_bounds__(MRSB_STEP_THREADS, MRSB_STEP_MINB) uav_step_kernel(DevState s, double dt, int k_sub_arg, int any_moment) {
+  const int k_sub = ONE ? 1 : k_sub_arg;
   const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= s.n) return;
   const int64_t ld = s.ld;
@@ -168,6 +179,7 @@ __global__ void __launch_bounds__(128) uav_step_kernel(DevState s, double dt, in
   uint32_t  flags                 = s.flags[i];
 
 #define LD(arr, row) (arr)[int64_t(row) * ld + i]
+#define ST(arr, row, val) (arr)[int64_t(row) * ld + i] = (val)
 
   // ---- load state -------------------------------------------------------------------------
   Vec3 x = mk(LD(s.st, 0), LD(s.st, 1), LD(s.st, 2));
@@ -412,31 +424,49 @@ __global__ void __launch_bounds__(128) uav_step_kernel(DevState s, double dt, in
       }
     }
 
-    // ======================= MultirotorModel::setInput (MM:392-410) ==========================
-    double usum = 0.0;
+    const bool last = ONE || (sub == k_sub - 1);
+    if (last) {  // controller state is final for this launch: store it now, not after the RK4 (register pressure)
+      if (on_pos) {
 #pragma unroll
-    for (int m = 0; m < MRSB_NM; m++) {
-      if (m < nm) {
-        double val = u[m];
-        if (!isfinite(val)) val = 0.0;
-        val  = val < 0.0 ? 0.0 : (val > 1.0 ? 1.0 : val);
-        u[m] = fma(rpm_range, val, min_rpm);
-        usum += u[m];
+        for (int r = 0; r < 6; r++) ST(s.pid, r, pd[r]);
+      }
+      if (on_vel) {
+#pragma unroll
+        for (int r = 6; r < 12; r++) ST(s.pid, r, pd[r]);
+      }
+      if (on_att) {
+#pragma unroll
+        for (int r = 12; r < 18; r++) ST(s.pid, r, pd[r]);
+      }
+      if (on_rate) {
+#pragma unroll
+        for (int r = 18; r < 24; r++) ST(s.pid, r, pd[r]);
       }
     }
 
-    // ======================= MultirotorModel::step (MM:220-286) ==============================
+    // ======================= MultirotorModel::setInput (MM:392-410) ==========================
+    // ... and the parts of MultirotorModel::step that only need the motor speeds: allocation
+    // (MM:332-335, frozen over the RK stages) and the first-order lag (MM:244-246), which does not
+    // depend on the integration result and is therefore done (and stored) before it.
     Frozen fz;
+    double usum = 0.0;
     {
       double t0 = 0, t1 = 0, t2 = 0, t3 = 0;
 #pragma unroll
       for (int m = 0; m < MRSB_NM; m++) {
         if (m < nm) {
+          double val = u[m];
+          if (!isfinite(val)) val = 0.0;
+          val = val < 0.0 ? 0.0 : (val > 1.0 ? 1.0 : val);
+          const double target = fma(rpm_range, val, min_rpm);
+          usum += target;
           const double sq = rpm[m] * rpm[m];
           t0 = fma(P->alloc[0][m], sq, t0);
           t1 = fma(P->alloc[1][m], sq, t1);
           t2 = fma(P->alloc[2][m], sq, t2);
           t3 = fma(P->alloc[3][m], sq, t3);
+          rpm[m] = filt * rpm[m] + (1.0 - filt) * target;
+          if (last) ST(s.rpm, m, rpm[m]);
         }
       }
       fz.g        = g;
@@ -507,11 +537,6 @@ __global__ void __launch_bounds__(128) uav_step_kernel(DevState s, double dt, in
       R = Rn;
     }
 
-    // MM:244-246 first-order motor lag, outside the ODE
-#pragma unroll
-    for (int m = 0; m < MRSB_NM; m++)
-      if (m < nm) rpm[m] = filt * rpm[m] + (1.0 - filt) * u[m];
-
     R = reortho(R);  // MM:249-253
 
     if (P->ground_enabled) {  // MM:256-262
@@ -540,7 +565,6 @@ __global__ void __launch_bounds__(128) uav_step_kernel(DevState s, double dt, in
   }
 
   // ---- store ------------------------------------------------------------------------------
-#define ST(arr, row, val) (arr)[int64_t(row) * ld + i] = (val)
   ST(s.st, 0, x.x);
   ST(s.st, 1, x.y);
   ST(s.st, 2, x.z);
@@ -559,25 +583,6 @@ __global__ void __launch_bounds__(128) uav_step_kernel(DevState s, double dt, in
   ST(s.st, 15, w.x);
   ST(s.st, 16, w.y);
   ST(s.st, 17, w.z);
-#pragma unroll
-  for (int m = 0; m < MRSB_NM; m++)
-    if (m < nm) ST(s.rpm, m, rpm[m]);
-  if (on_pos) {
-#pragma unroll
-    for (int r = 0; r < 6; r++) ST(s.pid, r, pd[r]);
-  }
-  if (on_vel) {
-#pragma unroll
-    for (int r = 6; r < 12; r++) ST(s.pid, r, pd[r]);
-  }
-  if (on_att) {
-#pragma unroll
-    for (int r = 12; r < 18; r++) ST(s.pid, r, pd[r]);
-  }
-  if (on_rate) {
-#pragma unroll
-    for (int r = 18; r < 24; r++) ST(s.pid, r, pd[r]);
-  }
   ST(s.imu, 0, imu.x);
   ST(s.imu, 1, imu.y);
   ST(s.imu, 2, imu.z);
@@ -603,9 +608,13 @@ __global__ void publish_positions_kernel(DevState s) {
 
 template <int NM_T, int MODE_T>
 void launch_one(const DevState& s, double dt, int k, int any_moment, cudaStream_t st) {
-  const int      threads = 128;
+  const int      threads = MRSB_STEP_THREADS;
   const unsigned blocks  = unsigned((s.n + threads - 1) / threads);
-  uav_step_kernel<NM_T, MODE_T><<<blocks, threads, 0, st>>>(s, dt, k, any_moment);
+  if (k == 1) {
+    uav_step_kernel<NM_T, MODE_T, true><<<blocks, threads, 0, st>>>(s, dt, k, any_moment);
+  } else {
+    uav_step_kernel<NM_T, MODE_T, false><<<blocks, threads, 0, st>>>(s, dt, k, any_moment);
+  }
 }
 
 template <int NM_T>
