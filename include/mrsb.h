@@ -266,13 +266,21 @@ int mrsb_publish_positions(mrsb_handle h);
 int mrsb_handle_collisions_gathered(mrsb_handle h);
 
 /* ---- zero-copy access for device-resident callers (RL loops) -------------------------------
- * Device pointers into the structure-of-arrays state; component c of UAV i is at ptr[c*ld + i].
- * x:3 v:3 R:9 (col-major) omega:3 rpm:MRSB_MAX_MOTORS rows.  Valid until mrsb_destroy. */
+ * Device pointers into the library's tiled structure-of-arrays state.  Every per-UAV array is cut
+ * into tiles of `tile` (=128) consecutive UAVs; component c of UAV i of an array with R rows is at
+ *     ptr[((i / tile) * R + c) * tile + i % tile].
+ * state: R = state_rows = 18 (x 0-2, v 3-5, R column-major 6-14, omega 15-17 — the reference's
+ * InternalState order, MM:204-214); motor_rpm: R = MRSB_MAX_MOTORS; imu_acc, ext_force: R = 3.
+ * flags[i] bit 0 = crashed; input_mode[i] = INPUT_MODE.  Valid until mrsb_destroy. */
 typedef struct mrsb_device_view {
-  int64_t ld; /* leading dimension (padded n_local) */
-  double *x, *v, *R, *omega, *motor_rpm, *imu_acc, *ext_force;
-  int32_t* crashed;
-  uint8_t* input_mode;
+  int32_t   tile;
+  int32_t   state_rows;
+  double*   state;
+  double*   motor_rpm;
+  double*   imu_acc;
+  double*   ext_force;
+  uint32_t* flags;
+  uint8_t*  input_mode;
 } mrsb_device_view;
 int mrsb_get_device_view(mrsb_handle h, mrsb_device_view* out);
 

@@ -39,8 +39,8 @@ class CreateInfo(C.Structure):
 
 
 class DeviceView(C.Structure):
-    _fields_ = [("ld", C.c_int64), ("x", C.c_void_p), ("v", C.c_void_p), ("R", C.c_void_p), ("omega", C.c_void_p), ("motor_rpm", C.c_void_p),
-                ("imu_acc", C.c_void_p), ("ext_force", C.c_void_p), ("crashed", C.c_void_p), ("input_mode", C.c_void_p)]
+    _fields_ = [("tile", C.c_int32), ("state_rows", C.c_int32), ("state", C.c_void_p), ("motor_rpm", C.c_void_p), ("imu_acc", C.c_void_p),
+                ("ext_force", C.c_void_p), ("flags", C.c_void_p), ("input_mode", C.c_void_p)]
 
 
 # every symbol include/mrsb.h declares: name -> (restype, argtypes)

@@ -528,7 +528,8 @@ int mrsb_clear_input(mrsb_handle h, int64_t n, const int32_t* idx) {
 }
 
 // host rows -> SoA rows [row0, row0+rows) of `dst`; then OR `flag` into the per-UAV flags
-static int put_rows(mrsb_sim* h, double* dst, int rows, int64_t n, const int32_t* idx, const double* payload, int stride, uint32_t or_flag) {
+static int put_rows(mrsb_sim* h, double* dst, int rows_total, int row0, int rows, int64_t n, const int32_t* idx, const double* payload, int stride,
+                    uint32_t or_flag) {
   const int32_t* d_idx = nullptr;
   int            rc    = stage_idx(h, n, idx, &d_idx);
   if (rc) return rc;
@@ -538,13 +539,13 @@ static int put_rows(mrsb_sim* h, double* dst, int rows, int64_t n, const int32_t
   rc                 = ensure_stage(h, bytes);
   if (rc) return rc;
   CU(cudaMemcpyAsync(h->d_stage, payload, bytes, cudaMemcpyHostToDevice, h->stream));
-  h->n_launches += launch_scatter_rows(dst, h->ds.ld, rows, n, d_idx, reinterpret_cast<const double*>(h->d_stage), stride, 0, h->stream);
+  h->n_launches += launch_scatter_rows(dst, rows_total, row0, rows, n, d_idx, reinterpret_cast<const double*>(h->d_stage), stride, h->stream);
   if (or_flag) h->n_launches += launch_flag_update(h->ds, n, d_idx, 0xffffffffu, or_flag, h->stream);
   CU(cudaGetLastError());
   return MRSB_OK;
 }
 
-static int get_rows(mrsb_sim* h, const double* src, int rows, int64_t n, const int32_t* idx, double* out) {
+static int get_rows(mrsb_sim* h, const double* src, int rows_total, int row0, int rows, int64_t n, const int32_t* idx, double* out) {
   const int32_t* d_idx = nullptr;
   int            rc    = stage_idx(h, n, idx, &d_idx);
   if (rc) return rc;
@@ -552,7 +553,7 @@ static int get_rows(mrsb_sim* h, const double* src, int rows, int64_t n, const i
   const size_t bytes = sizeof(double) * size_t(n) * size_t(rows);
   rc                 = ensure_stage(h, bytes);
   if (rc) return rc;
-  h->n_launches += launch_gather_rows(src, h->ds.ld, rows, n, d_idx, reinterpret_cast<double*>(h->d_stage), rows, 0, h->stream);
+  h->n_launches += launch_gather_rows(src, rows_total, row0, rows, n, d_idx, reinterpret_cast<double*>(h->d_stage), rows, h->stream);
   CU(cudaMemcpyAsync(out, h->d_stage, bytes, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   return MRSB_OK;
@@ -560,19 +561,19 @@ static int get_rows(mrsb_sim* h, const double* src, int rows, int64_t n, const i
 
 int mrsb_set_feedforward_acceleration_hdg_rate(mrsb_handle h, int64_t n, const int32_t* idx, const double* payload) {
   GUARD(h);
-  return put_rows(h, h->ds.ff + FF_ACC_HDG_RATE * h->ds.ld, 4, n, idx, payload, 4, FLAG_FF_ACC_HDG_RATE);
+  return put_rows(h, h->ds.ff, FF_ROWS, FF_ACC_HDG_RATE, 4, n, idx, payload, 4, FLAG_FF_ACC_HDG_RATE);
 }
 int mrsb_set_feedforward_acceleration_hdg(mrsb_handle h, int64_t n, const int32_t* idx, const double* payload) {
   GUARD(h);
-  return put_rows(h, h->ds.ff + FF_ACC_HDG * h->ds.ld, 3, n, idx, payload, 4, FLAG_FF_ACC_HDG);
+  return put_rows(h, h->ds.ff, FF_ROWS, FF_ACC_HDG, 3, n, idx, payload, 4, FLAG_FF_ACC_HDG);
 }
 int mrsb_set_feedforward_velocity_hdg(mrsb_handle h, int64_t n, const int32_t* idx, const double* payload) {
   GUARD(h);
-  return put_rows(h, h->ds.ff + FF_VEL_HDG * h->ds.ld, 3, n, idx, payload, 4, FLAG_FF_VEL_HDG);
+  return put_rows(h, h->ds.ff, FF_ROWS, FF_VEL_HDG, 3, n, idx, payload, 4, FLAG_FF_VEL_HDG);
 }
 int mrsb_set_feedforward_velocity_hdg_rate(mrsb_handle h, int64_t n, const int32_t* idx, const double* payload) {
   GUARD(h);
-  return put_rows(h, h->ds.ff + FF_VEL_HDG_RATE * h->ds.ld, 3, n, idx, payload, 4, FLAG_FF_VEL_HDG_RATE);
+  return put_rows(h, h->ds.ff, FF_ROWS, FF_VEL_HDG_RATE, 3, n, idx, payload, 4, FLAG_FF_VEL_HDG_RATE);
 }
 int mrsb_clear_feedforward(mrsb_handle h, int64_t n, const int32_t* idx) {
   GUARD(h);
@@ -658,13 +659,12 @@ int mrsb_run(mrsb_handle h, double dt, int32_t k_substeps, int32_t n_ticks, int3
 // ------------------------------------------------------------------------------------------
 int mrsb_get_state(mrsb_handle h, int64_t n, const int32_t* idx, double* x, double* v, double* R, double* omega, double* motor_rpm) {
   GUARD(h);
-  const int64_t ld = h->ds.ld;
-  int           rc = MRSB_OK;
-  if (x && !rc) rc = get_rows(h, h->ds.st + 0 * ld, 3, n, idx, x);
-  if (v && !rc) rc = get_rows(h, h->ds.st + 3 * ld, 3, n, idx, v);
-  if (R && !rc) rc = get_rows(h, h->ds.st + 6 * ld, 9, n, idx, R);
-  if (omega && !rc) rc = get_rows(h, h->ds.st + 15 * ld, 3, n, idx, omega);
-  if (motor_rpm && !rc) rc = get_rows(h, h->ds.rpm, MRSB_NM, n, idx, motor_rpm);
+  int rc = MRSB_OK;
+  if (x && !rc) rc = get_rows(h, h->ds.st, ST_ROWS, 0, 3, n, idx, x);
+  if (v && !rc) rc = get_rows(h, h->ds.st, ST_ROWS, 3, 3, n, idx, v);
+  if (R && !rc) rc = get_rows(h, h->ds.st, ST_ROWS, 6, 9, n, idx, R);
+  if (omega && !rc) rc = get_rows(h, h->ds.st, ST_ROWS, 15, 3, n, idx, omega);
+  if (motor_rpm && !rc) rc = get_rows(h, h->ds.rpm, MRSB_NM, 0, MRSB_NM, n, idx, motor_rpm);
   return rc;
 }
 
@@ -684,25 +684,24 @@ int mrsb_get_v_prev(mrsb_handle h, int64_t n, const int32_t* idx, double* v_prev
 
 int mrsb_get_imu_acceleration(mrsb_handle h, int64_t n, const int32_t* idx, double* acc) {
   GUARD(h);
-  return get_rows(h, h->ds.imu, 3, n, idx, acc);
+  return get_rows(h, h->ds.imu, F3_ROWS, 0, 3, n, idx, acc);
 }
 
 int mrsb_set_state(mrsb_handle h, int64_t n, const int32_t* idx, const double* x, const double* v, const double* R, const double* omega,
                    const double* motor_rpm) {
   GUARD(h);
-  const int64_t ld = h->ds.ld;
-  int           rc = MRSB_OK;
+  int rc = MRSB_OK;
   if (v) {
     const int32_t* d_idx = nullptr;
     rc                   = stage_idx(h, n, idx, &d_idx);
     if (rc) return rc;
     h->n_launches += launch_stash_vprev(h->ds, n, d_idx, h->stream);
   }
-  if (x && !rc) rc = put_rows(h, h->ds.st + 0 * ld, 3, n, idx, x, 3, 0);
-  if (v && !rc) rc = put_rows(h, h->ds.st + 3 * ld, 3, n, idx, v, 3, 0);
-  if (R && !rc) rc = put_rows(h, h->ds.st + 6 * ld, 9, n, idx, R, 9, 0);
-  if (omega && !rc) rc = put_rows(h, h->ds.st + 15 * ld, 3, n, idx, omega, 3, 0);
-  if (motor_rpm && !rc) rc = put_rows(h, h->ds.rpm, MRSB_NM, n, idx, motor_rpm, MRSB_NM, 0);
+  if (x && !rc) rc = put_rows(h, h->ds.st, ST_ROWS, 0, 3, n, idx, x, 3, 0);
+  if (v && !rc) rc = put_rows(h, h->ds.st, ST_ROWS, 3, 3, n, idx, v, 3, 0);
+  if (R && !rc) rc = put_rows(h, h->ds.st, ST_ROWS, 6, 9, n, idx, R, 9, 0);
+  if (omega && !rc) rc = put_rows(h, h->ds.st, ST_ROWS, 15, 3, n, idx, omega, 3, 0);
+  if (motor_rpm && !rc) rc = put_rows(h, h->ds.rpm, MRSB_NM, 0, MRSB_NM, n, idx, motor_rpm, MRSB_NM, 0);
   if (x && !rc) h->n_launches += launch_publish_positions(h->ds, h->stream);
   return rc;
 }
@@ -773,16 +772,16 @@ int mrsb_has_crashed(mrsb_handle h, int64_t n, const int32_t* idx, int32_t* cras
 
 int mrsb_apply_force(mrsb_handle h, int64_t n, const int32_t* idx, const double* force) {
   GUARD(h);
-  return put_rows(h, h->ds.fext, 3, n, idx, force, 3, 0);
+  return put_rows(h, h->ds.fext, F3_ROWS, 0, 3, n, idx, force, 3, 0);
 }
 int mrsb_get_external_force(mrsb_handle h, int64_t n, const int32_t* idx, double* force) {
   GUARD(h);
-  return get_rows(h, h->ds.fext, 3, n, idx, force);
+  return get_rows(h, h->ds.fext, F3_ROWS, 0, 3, n, idx, force);
 }
 int mrsb_set_external_moment(mrsb_handle h, int64_t n, const int32_t* idx, const double* moment) {
   GUARD(h);
   h->any_moment = true;
-  return put_rows(h, h->ds.mext, 3, n, idx, moment, 3, 0);
+  return put_rows(h, h->ds.mext, F3_ROWS, 0, 3, n, idx, moment, 3, 0);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1015,16 +1014,13 @@ int mrsb_publish_positions(mrsb_handle h) {
 
 int mrsb_get_device_view(mrsb_handle h, mrsb_device_view* out) {
   GUARD(h);
-  const int64_t ld = h->ds.ld;
-  out->ld          = ld;
-  out->x           = h->ds.st;
-  out->v           = h->ds.st + 3 * ld;
-  out->R           = h->ds.st + 6 * ld;
-  out->omega       = h->ds.st + 15 * ld;
+  out->tile        = MRSB_TILE;
+  out->state       = h->ds.st;
+  out->state_rows  = ST_ROWS;
   out->motor_rpm   = h->ds.rpm;
   out->imu_acc     = h->ds.imu;
   out->ext_force   = h->ds.fext;
-  out->crashed     = reinterpret_cast<int32_t*>(h->ds.flags);
+  out->flags       = h->ds.flags;
   out->input_mode  = h->ds.mode;
   return MRSB_OK;
 }

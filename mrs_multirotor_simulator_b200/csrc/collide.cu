@@ -283,9 +283,9 @@ __global__ void __launch_bounds__(128) collide_kernel(DevState s, DevGrid g, int
   }
 
   // SIM:356-358: forces replace external_force_ for the next tick (zero in crash mode, SIM:315-319)
-  s.fext[0 * s.ld + li] = fx;
-  s.fext[1 * s.ld + li] = fy;
-  s.fext[2 * s.ld + li] = fz;
+  s.fext[tix(F3_ROWS, 0, li)] = fx;
+  s.fext[tix(F3_ROWS, 1, li)] = fy;
+  s.fext[tix(F3_ROWS, 2, li)] = fz;
   if (crashed_me) s.flags[li] |= FLAG_CRASHED;
 }
 

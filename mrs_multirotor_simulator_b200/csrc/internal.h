@@ -1,9 +1,12 @@
 // internal.h — device data layout and host bookkeeping of libmrsb (not part of the public ABI).
 //
-// HBM layout: structure of arrays, one double array per state component with
-// leading dimension `ld` (n_local rounded up to 128), so thread i of a warp touches element i of
-// every component array: every load/store of the stepping kernel is a fully coalesced 256-byte
-// warp transaction.
+// HBM layout: tiled structure of arrays ("AoSoA").  Every per-UAV array is cut into
+// tiles of MRSB_TILE = 128 consecutive UAVs; inside a tile the ROWS components are stored row after
+// row, 128 doubles (1 KiB) each:   element(row, i) = base[((i / 128) * ROWS + row) * 128 + i % 128].
+// A 128-thread CTA of the stepping kernel owns exactly one tile: its loads and stores are fully
+// coalesced 256-byte warp transactions at COMPILE-TIME offsets from one tile pointer (no per-access
+// address arithmetic), and the tile is one contiguous chunk of HBM (DRAM page locality, and one
+// bulk copy per array when it is staged through shared memory).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -11,6 +14,16 @@
 #include "../../include/mrsb.h"
 
 #define MRSB_NM MRSB_MAX_MOTORS
+#define MRSB_TILE 128
+
+// index of component `row` of UAV `i` in a tiled array with `rows` components
+static __host__ __device__ __forceinline__ int64_t tix(int rows, int row, int64_t i) {
+  return ((i >> 7) * rows + row) * MRSB_TILE + (i & (MRSB_TILE - 1));
+}
+// rows of each per-UAV array
+#define ST_ROWS 18
+#define VPREV_ROWS 3
+#define F3_ROWS 3
 
 // per-UAV flag bits
 #define FLAG_CRASHED 1u        // UavSystem::crashed_ (US:80)
@@ -42,7 +55,7 @@ struct DevParams {
   int32_t ground_enabled;
   int32_t mixer_desaturation;
   int32_t j_diagonal;
-  double  g, mass, inv_mass, kf_n /* kf*n_motors */, min_rpm, rpm_range, inv_rpm_range, neg_inv_tau, air_k /* c*pi*l*l */, ground_z,
+  double  g, mass, inv_mass, inv_kf_n /* 1/(kf*n_motors) */, min_rpm, rpm_range, inv_rpm_range, neg_inv_tau, air_k /* c*pi*l*l */, ground_z,
       takeoff_rpm /* 0.9*hover_rpm, MM:266-267 */;
   double arm_length, prop_radius;  // collision geometry (SIM:342)
   double J[9], Jinv[9];            // row-major
@@ -57,8 +70,8 @@ struct DevParams {
 // Device pointers of one shard.  Passed to kernels by value.
 struct DevState {
   int64_t  n;   // UAVs in this shard
-  int64_t  ld;  // leading dimension of all SoA arrays
-  double*  st;  // [18][ld] x(0-2) v(3-5) R col-major(6-14) omega(15-17)  == InternalState MM:204-214
+  int64_t  ld;  // n rounded up to a whole number of tiles (allocation size per row)
+  double*  st;  // tiled, ST_ROWS rows: x(0-2) v(3-5) R col-major(6-14) omega(15-17)  == InternalState MM:204-214
   double*  vprev;  // [3][ld]  only meaningful where FLAG_VPREV is set
   double*  rpm;    // [MRSB_NM][ld]
   double*  pid;    // [PID_ROWS][ld]
@@ -99,9 +112,10 @@ size_t collide_tmp_bytes(int64_t n_global);
 int launch_publish_positions(const DevState& s, cudaStream_t stream);
 
 int launch_scatter_input(const DevState& s, int mode, int64_t n, const int32_t* idx_dev, const double* payload_dev, int stride, cudaStream_t stream);
-int launch_scatter_rows(double* dst, int64_t ld, int rows, int64_t n, const int32_t* idx_dev, const double* payload_dev, int stride, int col0,
+// payload[k][0..rows) <-> rows [row0, row0+rows) of a tiled array with `rows_total` components
+int launch_scatter_rows(double* dst, int rows_total, int row0, int rows, int64_t n, const int32_t* idx_dev, const double* payload_dev, int stride,
                         cudaStream_t stream);
-int launch_gather_rows(const double* src, int64_t ld, int rows, int64_t n, const int32_t* idx_dev, double* out_dev, int stride, int col0,
+int launch_gather_rows(const double* src, int rows_total, int row0, int rows, int64_t n, const int32_t* idx_dev, double* out_dev, int stride,
                        cudaStream_t stream);
 int launch_flag_update(const DevState& s, int64_t n, const int32_t* idx_dev, uint32_t and_mask, uint32_t or_mask, cudaStream_t stream);
 int launch_gather_u32(const uint32_t* src, int64_t n, const int32_t* idx_dev, uint32_t* out_dev, cudaStream_t stream);

@@ -20,12 +20,12 @@ __global__ void scatter_input_kernel(DevState s, int mode, int64_t n, const int3
   if (i < 0 || i >= s.n) return;
   const double* p    = payload + k * stride;
   const int     rows = mode == MRSB_ACTUATOR_CMD ? MRSB_NM : (mode == MRSB_ATTITUDE_CMD ? 10 : (mode == MRSB_TILT_HDG_RATE_CMD ? 5 : 4));
-  for (int r = 0; r < rows; r++) s.cmd[int64_t(r) * s.ld + i] = r < stride ? p[r] : 0.0;
+  for (int r = 0; r < rows; r++) s.cmd[tix(CMD_ROWS, r, i)] = r < stride ? p[r] : 0.0;
   if (mode == MRSB_POSITION_CMD || mode == MRSB_VELOCITY_HDG_CMD || mode == MRSB_ACCELERATION_HDG_CMD) {
     double sn, cs;
     sincos(p[3], &sn, &cs);
-    s.cmd[int64_t(CMD_COS) * s.ld + i] = cs;
-    s.cmd[int64_t(CMD_SIN) * s.ld + i] = sn;
+    s.cmd[tix(CMD_ROWS, CMD_COS, i)] = cs;
+    s.cmd[tix(CMD_ROWS, CMD_SIN, i)] = sn;
   }
   s.mode[i] = uint8_t(mode);
 }
@@ -38,21 +38,21 @@ __global__ void set_mode_kernel(DevState s, int64_t n, const int32_t* __restrict
   s.mode[i] = uint8_t(mode);
 }
 
-// payload[k][col0 .. col0+rows) -> dst[row][i]
-__global__ void scatter_rows_kernel(double* __restrict__ dst, int64_t ld, int rows, int64_t n, const int32_t* __restrict__ idx,
-                                    const double* __restrict__ payload, int stride, int col0) {
+// payload[k][0 .. rows) -> rows [row0, row0+rows) of UAV i
+__global__ void scatter_rows_kernel(double* __restrict__ dst, int rows_total, int row0, int rows, int64_t n, const int32_t* __restrict__ idx,
+                                    const double* __restrict__ payload, int stride) {
   const int64_t k = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (k >= n) return;
   const int64_t i = at(idx, k);
-  for (int r = 0; r < rows; r++) dst[int64_t(r) * ld + i] = payload[k * stride + col0 + r];
+  for (int r = 0; r < rows; r++) dst[tix(rows_total, row0 + r, i)] = payload[k * stride + r];
 }
 
-__global__ void gather_rows_kernel(const double* __restrict__ src, int64_t ld, int rows, int64_t n, const int32_t* __restrict__ idx,
-                                   double* __restrict__ out, int stride, int col0) {
+__global__ void gather_rows_kernel(const double* __restrict__ src, int rows_total, int row0, int rows, int64_t n, const int32_t* __restrict__ idx,
+                                   double* __restrict__ out, int stride) {
   const int64_t k = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (k >= n) return;
   const int64_t i = at(idx, k);
-  for (int r = 0; r < rows; r++) out[k * stride + col0 + r] = src[int64_t(r) * ld + i];
+  for (int r = 0; r < rows; r++) out[k * stride + r] = src[tix(rows_total, row0 + r, i)];
 }
 
 __global__ void flag_update_kernel(DevState s, int64_t n, const int32_t* __restrict__ idx, uint32_t and_mask, uint32_t or_mask) {
@@ -80,24 +80,23 @@ __global__ void set_state_pos_kernel(DevState s, int64_t n, const int32_t* __res
   const int64_t k = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (k >= n) return;
   const int64_t i  = at(idx, k);
-  const int64_t ld = s.ld;
   const double  px = xyz ? xyz[3 * k] : 0.0, py = xyz ? xyz[3 * k + 1] : 0.0, pz = xyz ? xyz[3 * k + 2] : 0.0;
   double        sn, cs;
   sincos(hdg ? -hdg[k] : -0.0, &sn, &cs);
-  s.st[0 * ld + i] = px;
-  s.st[1 * ld + i] = py;
-  s.st[2 * ld + i] = pz;
+  s.st[tix(ST_ROWS, 0, i)] = px;
+  s.st[tix(ST_ROWS, 1, i)] = py;
+  s.st[tix(ST_ROWS, 2, i)] = pz;
   s.initz[i]       = pz;
   // column-major R = [[c,-s,0],[s,c,0],[0,0,(1-c)+c]] for angle -heading (Eigen AngleAxis::toRotationMatrix)
-  s.st[6 * ld + i]  = cs;
-  s.st[7 * ld + i]  = sn;
-  s.st[8 * ld + i]  = 0.0;
-  s.st[9 * ld + i]  = -sn;
-  s.st[10 * ld + i] = cs;
-  s.st[11 * ld + i] = 0.0;
-  s.st[12 * ld + i] = 0.0;
-  s.st[13 * ld + i] = 0.0;
-  s.st[14 * ld + i] = (1.0 - cs) + cs;
+  s.st[tix(ST_ROWS, 6, i)]  = cs;
+  s.st[tix(ST_ROWS, 7, i)]  = sn;
+  s.st[tix(ST_ROWS, 8, i)]  = 0.0;
+  s.st[tix(ST_ROWS, 9, i)]  = -sn;
+  s.st[tix(ST_ROWS, 10, i)] = cs;
+  s.st[tix(ST_ROWS, 11, i)] = 0.0;
+  s.st[tix(ST_ROWS, 12, i)] = 0.0;
+  s.st[tix(ST_ROWS, 13, i)] = 0.0;
+  s.st[tix(ST_ROWS, 14, i)] = (1.0 - cs) + cs;
   double* gp        = s.gpos + 3 * (s.shard_begin + i);
   gp[0]             = px;
   gp[1]             = py;
@@ -110,7 +109,7 @@ __global__ void stash_vprev_kernel(DevState s, int64_t n, const int32_t* __restr
   if (k >= n) return;
   const int64_t i = at(idx, k);
   if (s.flags[i] & FLAG_VPREV) return;
-  for (int r = 0; r < 3; r++) s.vprev[int64_t(r) * s.ld + i] = s.st[int64_t(3 + r) * s.ld + i];
+  for (int r = 0; r < 3; r++) s.vprev[tix(VPREV_ROWS, r, i)] = s.st[tix(ST_ROWS, 3 + r, i)];
   s.flags[i] |= FLAG_VPREV;
 }
 
@@ -119,14 +118,14 @@ __global__ void gather_vprev_kernel(DevState s, int64_t n, const int32_t* __rest
   if (k >= n) return;
   const int64_t i  = at(idx, k);
   const bool    ov = s.flags[i] & FLAG_VPREV;
-  for (int r = 0; r < 3; r++) out[3 * k + r] = ov ? s.vprev[int64_t(r) * s.ld + i] : s.st[int64_t(3 + r) * s.ld + i];
+  for (int r = 0; r < 3; r++) out[3 * k + r] = ov ? s.vprev[tix(VPREV_ROWS, r, i)] : s.st[tix(ST_ROWS, 3 + r, i)];
 }
 
 __global__ void reset_pid_kernel(DevState s, int64_t n, const int32_t* __restrict__ idx, int row0, int rows) {
   const int64_t k = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (k >= n) return;
   const int64_t i = at(idx, k);
-  for (int r = row0; r < row0 + rows; r++) s.pid[int64_t(r) * s.ld + i] = 0.0;
+  for (int r = row0; r < row0 + rows; r++) s.pid[tix(PID_ROWS, r, i)] = 0.0;
 }
 
 __global__ void set_pset_kernel(int32_t* __restrict__ pset, int64_t n, const int32_t* __restrict__ idx, int64_t offset,
@@ -148,15 +147,15 @@ int launch_set_mode(const DevState& s, int64_t n, const int32_t* idx, int mode, 
   set_mode_kernel<<<nblk(n), 256, 0, st>>>(s, n, idx, mode);
   return 1;
 }
-int launch_scatter_rows(double* dst, int64_t ld, int rows, int64_t n, const int32_t* idx, const double* payload, int stride, int col0,
+int launch_scatter_rows(double* dst, int rows_total, int row0, int rows, int64_t n, const int32_t* idx, const double* payload, int stride,
                         cudaStream_t st) {
   if (n <= 0) return 0;
-  scatter_rows_kernel<<<nblk(n), 256, 0, st>>>(dst, ld, rows, n, idx, payload, stride, col0);
+  scatter_rows_kernel<<<nblk(n), 256, 0, st>>>(dst, rows_total, row0, rows, n, idx, payload, stride);
   return 1;
 }
-int launch_gather_rows(const double* src, int64_t ld, int rows, int64_t n, const int32_t* idx, double* out, int stride, int col0, cudaStream_t st) {
+int launch_gather_rows(const double* src, int rows_total, int row0, int rows, int64_t n, const int32_t* idx, double* out, int stride, cudaStream_t st) {
   if (n <= 0) return 0;
-  gather_rows_kernel<<<nblk(n), 256, 0, st>>>(src, ld, rows, n, idx, out, stride, col0);
+  gather_rows_kernel<<<nblk(n), 256, 0, st>>>(src, rows_total, row0, rows, n, idx, out, stride);
   return 1;
 }
 int launch_flag_update(const DevState& s, int64_t n, const int32_t* idx, uint32_t and_mask, uint32_t or_mask, cudaStream_t st) {

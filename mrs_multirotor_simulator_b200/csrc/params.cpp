@@ -135,7 +135,7 @@ void mrsb_derive(const mrsb_model_params& mp, const mrsb_controller_params& cp, 
   d->g                  = mp.g;
   d->mass               = mp.mass;
   d->inv_mass           = 1.0 / mp.mass;
-  d->kf_n               = mp.kf * mp.n_motors;
+  d->inv_kf_n           = 1.0 / (mp.kf * mp.n_motors);
   d->min_rpm            = mp.min_rpm;
   d->rpm_range          = mp.max_rpm - mp.min_rpm;
   d->inv_rpm_range      = 1.0 / (mp.max_rpm - mp.min_rpm);

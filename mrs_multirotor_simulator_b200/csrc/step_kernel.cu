@@ -17,17 +17,50 @@
 //   * the SO(3) error needs only the six off-diagonal dot products of Rd^T R;
 //   * RK4 keeps a running weighted sum instead of four stored slopes, and skips the zero-
 //     coefficient terms odeint multiplies through (generic_rk_operations.hpp:30-68);
+//   * reciprocals, reciprocal square roots and square roots are the hardware approximation
+//     (MUFU.RCP64H / MUFU.RSQ64H, 2^-23) followed by ONE third-order Newton step in FP64 (error
+//     ~2^-66 before the final rounding): branch-free, no slow-path calls; a division is a
+//     multiplication by such a reciprocal (<= 2 ulp instead of correctly rounded);
+//   * the NaN -> 0 scrub of the slopes (MM:361-365) and the NaN -> restore check (MM:228-233) first
+//     screen the exponent fields with integer max (any Inf/NaN?) and only then do the exact test;
 //   * FMA contraction is on.
 // All of these change results only at rounding level (<= a few ulp per operation); parity with the
 // CPU oracle is asserted within the tolerances of DESIGN.md §5 by tests/test_step_parity.py.
 //
 // Roofline: ~0.4-0.8 kB of state traffic and ~2.6 kFLOP (as-written census) per
 // UAV-step; FP64-pipe bound on B200 once K >= 2, close to balanced at K = 1.
+#include <cstdlib>
+
 #include "internal.h"
 
 namespace {
 
 #define DEV __device__ __forceinline__
+
+// 1/sqrt(x) for normal positive x: MUFU.RSQ64H seed (rel. error 2^-22.9) + one third-order step.
+// x = 0 / negative / Inf / NaN give NaN or Inf garbage, as does the reference's Cholesky there.
+DEV double rsqrt_fast(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double t = x * y;
+  const double e = fma(-t, y, 1.0);
+  const double p = fma(0.375, e, 0.5);
+  return fma(y * e, p, y);
+}
+// 1/b for normal b: MUFU.RCP64H seed (2^-23) + one third-order step
+DEV double rcp_fast(double b) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+  const double e = fma(-b, r, 1.0);
+  const double p = fma(e, e, e);
+  return fma(r, p, r);
+}
+// sqrt(x); exact IEEE path only for the rare tiny / zero / negative / non-finite arguments
+DEV double sqrt_fast(double x) {
+  if (x > 1e-290 && x < 1e300) return x * rsqrt_fast(x);
+  return sqrt(x);
+}
+DEV unsigned expo(double v) { return unsigned(__double2hiint(v)) & 0x7ff00000u; }
 
 struct Vec3 {
   double x, y, z;
@@ -48,12 +81,11 @@ DEV Vec3   fma3(Vec3 a, double s, Vec3 b) { return mk(fma(a.x, s, b.x), fma(a.y,
 // Eigen normalized(): divide by the norm only if the squared norm is positive
 DEV Vec3 normalized(Vec3 a) {
   const double z = dot(a, a);
-  if (z > 0.0) {
-    const double r = 1.0 / sqrt(z);
-    return a * r;
-  }
+  if (z > 1e-290 && z < 1e300) return a * rsqrt_fast(z);
+  if (z > 0.0) return a * (1.0 / sqrt(z));
   return a;
 }
+DEV unsigned expo3(Vec3 a) { return max(expo(a.x), max(expo(a.y), expo(a.z))); }
 DEV bool isnan3(Vec3 a) { return (a.x != a.x) | (a.y != a.y) | (a.z != a.z); }
 DEV Vec3 nan0(Vec3 a) { return mk(a.x != a.x ? 0.0 : a.x, a.y != a.y ? 0.0 : a.y, a.z != a.z ? 0.0 : a.z); }
 
@@ -61,18 +93,43 @@ struct Rot {
   Vec3 c0, c1, c2;  // columns
 };
 
-// R * chol(R^T R)^-1  with chol = lower Cholesky factor (MM:314-316 / MM:249-253).
+// R * chol(R^T R)^-1  with chol = lower Cholesky factor L (MM:314-316 / MM:249-253); L^-1 is the
+// closed form for a lower-triangular 3x3.  MRSB_CHOL_PARALLEL=1 is an experiment that derives the
+// three pivots from the leading minors of G so that the reciprocal square roots are independent;
+// measured on B200 it is not faster than the textbook recurrence (profiles/README.md), which
+// stays the default.
+#ifndef MRSB_CHOL_PARALLEL
+#define MRSB_CHOL_PARALLEL 0
+#endif
 DEV Rot reortho(const Rot& R) {
   const double g00 = dot(R.c0, R.c0), g10 = dot(R.c1, R.c0), g20 = dot(R.c2, R.c0);
   const double g11 = dot(R.c1, R.c1), g21 = dot(R.c2, R.c1), g22 = dot(R.c2, R.c2);
-  const double i00 = rsqrt(g00);
+#if !MRSB_CHOL_PARALLEL
+  const double i00 = rsqrt_fast(g00);
   const double l10 = g10 * i00, l20 = g20 * i00;
   const double d1  = g11 - l10 * l10;
-  const double i11 = rsqrt(d1);
+  const double i11 = rsqrt_fast(d1);
   const double l11 = d1 * i11;
   const double l21 = (g21 - l20 * l10) * i11;
   const double d2  = g22 - (l20 * l20 + l21 * l21);
-  const double i22 = rsqrt(d2);
+  const double i22 = rsqrt_fast(d2);
+#else
+  const double m1  = fma(g00, g11, -(g10 * g10));
+  const double c0  = fma(g11, g22, -(g21 * g21));
+  const double c1  = fma(g10, g22, -(g21 * g20));
+  const double c2  = fma(g10, g21, -(g11 * g20));
+  const double det = fma(g00, c0, fma(-g10, c1, g20 * c2));
+  const double i00 = rsqrt_fast(g00);
+  const double r1  = rsqrt_fast(m1);
+  const double rd  = rsqrt_fast(det);
+  const double s00 = g00 * i00;  // sqrt(g00)  = L00
+  const double s1  = m1 * r1;    // sqrt(m1)
+  const double i11 = s00 * r1;   // 1 / L11
+  const double l11 = s1 * i00;   // L11
+  const double i22 = s1 * rd;    // 1 / L22
+  const double l10 = g10 * i00, l20 = g20 * i00;
+  const double l21 = (g21 - l20 * l10) * i11;
+#endif
   const double a10 = -(l10 * i00) * i11;
   const double a21 = -(l21 * i11) * i22;
   const double a20 = (l10 * l21 - l20 * l11) * (i00 * i11 * i22);
@@ -97,12 +154,16 @@ struct Slope {
   Rot  dR;
 };
 
-// MultirotorModel::operator() (MM:301-366) without the x_dot = v rows (handled by the caller)
-DEV Slope derivative(Vec3 v, const Rot& Rraw, Vec3 w, const Frozen& f, const DevParams* __restrict__ P, bool jdiag, Vec3 Jd, Vec3 Jdi) {
-  Slope      k;
-  const Rot  R  = reortho(Rraw);
+// MultirotorModel::operator() (MM:301-366) without the x_dot = v rows (handled by the caller).
+// NaN slopes are scrubbed to zero element by element (MM:361-365): always when EXACT, otherwise only
+// after an integer screen of the exponent fields found something Inf/NaN.
+template <bool EXACT>
+DEV Slope derivative(Vec3 v, const Rot& Rraw, Vec3 w, const Frozen& f, const DevParams* __restrict__ P, bool jdiag, Vec3 Jd, Vec3 Jdi, unsigned& screen) {
+  Slope        k;
+  const Rot    R     = reortho(Rraw);
   const double vv    = dot(v, v);
-  const double speed = vv > 0.0 ? vv * rsqrt(vv) : 0.0;
+  const double sp    = vv * rsqrt_fast(vv);
+  const double speed = vv > 1e-290 ? sp : 0.0;  // |v| < 1e-145 m/s: the drag term is zero to 1e-290
   const double kd    = f.air_m * speed;
   k.dv = mk(fma(R.c2.x, f.thrust_m, f.f_m.x) - kd * v.x, fma(R.c2.y, f.thrust_m, f.f_m.y) - kd * v.y,
             (fma(R.c2.z, f.thrust_m, f.f_m.z) - f.g) - kd * v.z);
@@ -121,13 +182,76 @@ DEV Slope derivative(Vec3 v, const Rot& Rraw, Vec3 w, const Frozen& f, const Dev
     const Vec3    r  = f.tau - cross(w, Jw);
     k.dw = mk(Ji[0] * r.x + (Ji[1] * r.y + Ji[2] * r.z), Ji[3] * r.x + (Ji[4] * r.y + Ji[5] * r.z), Ji[6] * r.x + (Ji[7] * r.y + Ji[8] * r.z));
   }
-  // MM:361-365
-  k.dv    = nan0(k.dv);
-  k.dw    = nan0(k.dw);
-  k.dR.c0 = nan0(k.dR.c0);
-  k.dR.c1 = nan0(k.dR.c1);
-  k.dR.c2 = nan0(k.dR.c2);
+  if (EXACT) {
+    k.dv    = nan0(k.dv);
+    k.dw    = nan0(k.dw);
+    k.dR.c0 = nan0(k.dR.c0);
+    k.dR.c1 = nan0(k.dR.c1);
+    k.dR.c2 = nan0(k.dR.c2);
+  } else {
+    // screen: is any exponent field all ones, i.e. is anything Inf or NaN at all?  (rarely taken)
+    screen = max(max(expo3(k.dv), expo3(k.dw)), max(expo3(k.dR.c0), max(expo3(k.dR.c1), expo3(k.dR.c2))));
+    if (screen == 0x7ff00000u) {
+      k.dv    = nan0(k.dv);
+      k.dw    = nan0(k.dw);
+      k.dR.c0 = nan0(k.dR.c0);
+      k.dR.c1 = nan0(k.dR.c1);
+      k.dR.c2 = nan0(k.dR.c2);
+    }
+  }
   return k;
+}
+
+struct Rigid {
+  Vec3 x, v, w;
+  Rot  R;
+};
+
+// odeint's classic RK4 (ODE/stepper/runge_kutta4.hpp:42-95) as a running weighted sum.
+// Returns the non-finite screen of the four slope evaluations (always 0 when EXACT).
+template <bool EXACT>
+DEV unsigned rk4(const Rigid& a, Rigid& out, double dt, const Frozen& fz, const DevParams* __restrict__ P, bool jdiag, Vec3 Jd, Vec3 Jdi) {
+  unsigned     screen = 0;
+  const double h      = 0.5 * dt;
+  Slope        k      = derivative<EXACT>(a.v, a.R, a.w, fz, P, jdiag, Jd, Jdi, screen);
+  Vec3         sx = a.v, sv = k.dv, sw = k.dw;
+  Rot          sR = k.dR;
+  Vec3         vt = fma3(k.dv, h, a.v), wt = fma3(k.dw, h, a.w);
+  Rot          Rt;
+  Rt.c0 = fma3(k.dR.c0, h, a.R.c0);
+  Rt.c1 = fma3(k.dR.c1, h, a.R.c1);
+  Rt.c2 = fma3(k.dR.c2, h, a.R.c2);
+#pragma unroll
+  for (int stage = 0; stage < 2; stage++) {
+    const double c = stage == 0 ? h : dt;
+    k              = derivative<EXACT>(vt, Rt, wt, fz, P, jdiag, Jd, Jdi, screen);
+    sx             = fma3(vt, 2.0, sx);
+    sv             = fma3(k.dv, 2.0, sv);
+    sw             = fma3(k.dw, 2.0, sw);
+    sR.c0          = fma3(k.dR.c0, 2.0, sR.c0);
+    sR.c1          = fma3(k.dR.c1, 2.0, sR.c1);
+    sR.c2          = fma3(k.dR.c2, 2.0, sR.c2);
+    vt             = fma3(k.dv, c, a.v);
+    wt             = fma3(k.dw, c, a.w);
+    Rt.c0          = fma3(k.dR.c0, c, a.R.c0);
+    Rt.c1          = fma3(k.dR.c1, c, a.R.c1);
+    Rt.c2          = fma3(k.dR.c2, c, a.R.c2);
+  }
+  k  = derivative<EXACT>(vt, Rt, wt, fz, P, jdiag, Jd, Jdi, screen);
+  sx = sx + vt;
+  sv = sv + k.dv;
+  sw = sw + k.dw;
+  sR.c0 = sR.c0 + k.dR.c0;
+  sR.c1 = sR.c1 + k.dR.c1;
+  sR.c2 = sR.c2 + k.dR.c2;
+  const double h6 = dt * (1.0 / 6.0);
+  out.x    = fma3(sx, h6, a.x);
+  out.v    = fma3(sv, h6, a.v);
+  out.w    = fma3(sw, h6, a.w);
+  out.R.c0 = fma3(sR.c0, h6, a.R.c0);
+  out.R.c1 = fma3(sR.c1, h6, a.R.c1);
+  out.R.c2 = fma3(sR.c2, h6, a.R.c2);
+  return screen;
 }
 
 // PIDController::update (CTL/pid.hpp:67-96)
@@ -163,40 +287,94 @@ DEV Vec3 attitude_error(const Rot& Rd, const Rot& R) {
 #define MRSB_STEP_MINB 2
 #endif
 
+// ---- TMA / mbarrier plumbing for the staged kernel ---------------------------------------------
+DEV uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
+DEV void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+DEV void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+DEV void mbar_wait(uint64_t* bar, uint32_t phase) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "MRSB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra MRSB_DONE;\n"
+      "bra MRSB_WAIT;\n"
+      "MRSB_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(phase)
+      : "memory");
+}
+// 1-D bulk copy global -> shared through the TMA unit, completion counted on `bar`
+DEV void tma_load(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)), "l"(gmem_src),
+               "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// where one thread reads its UAV's inputs: tile base + lane, rows 128 doubles apart — either the
+// tile in HBM (direct kernel) or its copy in shared memory (staged kernel)
+struct TileIn {
+  const double *st, *rpm, *pid, *cmd, *fext;
+};
+
 // NM_T: motors per UAV if uniform over the batch (4/6/8), 0 = read per UAV.  MODE_T: INPUT_MODE if
 // uniform, -1 = read per UAV.  ONE: k_sub == 1 (no substep loop: PID state, commands and motor
-// speeds are dead after their single use, which is worth ~60 registers).
-template <int NM_T, int MODE_T, bool ONE>
-__global__ void __launch_bounds__(MRSB_STEP_THREADS, MRSB_STEP_MINB) uav_step_kernel(DevState s, double dt, int k_sub_arg, int any_moment) {
+// speeds are dead after their single use, which is worth ~60 registers).  `after_loads` runs once
+// per thread after the last read through `in` (the staged kernel re-arms its TMA there).
+template <int NM_T, int MODE_T, bool ONE, class Hook>
+DEV void step_uav(const DevState& s, const TileIn& in, const int64_t tile, const uint32_t flags0, const int32_t pset, const double dt,
+                  const int k_sub_arg, const int any_moment, Hook after_loads) {
   const int k_sub = ONE ? 1 : k_sub_arg;
-  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= s.n) return;
-  const int64_t ld = s.ld;
+  static_assert(MRSB_STEP_THREADS == MRSB_TILE, "one CTA per 128-UAV tile");
+  const int64_t i_raw = tile * MRSB_TILE + threadIdx.x;
+  const bool    valid = i_raw < s.n;  // lanes past the end of the last tile compute on padding and store nothing
+  const int64_t i     = valid ? i_raw : s.n - 1;
+  // tile base pointers: every access below is [pointer + compile-time offset]
+  const double* const t_st   = in.st;
+  const double* const t_rpm  = in.rpm;
+  const double* const t_pid  = in.pid;
+  const double* const t_cmd  = in.cmd;
+  const double* const t_fext = in.fext;
+  double* const o_st    = s.st + (tile * ST_ROWS) * MRSB_TILE + threadIdx.x;
+  double* const o_rpm   = s.rpm + (tile * MRSB_NM) * MRSB_TILE + threadIdx.x;
+  double* const o_pid   = s.pid + (tile * PID_ROWS) * MRSB_TILE + threadIdx.x;
+  double* const o_imu   = s.imu + (tile * F3_ROWS) * MRSB_TILE + threadIdx.x;
+  const double* const t_ff    = s.ff + (tile * FF_ROWS) * MRSB_TILE + threadIdx.x;
+  const double* const t_mext  = s.mext + (tile * F3_ROWS) * MRSB_TILE + threadIdx.x;
+  const double* const t_vprev = s.vprev + (tile * VPREV_ROWS) * MRSB_TILE + threadIdx.x;
 
-  const DevParams* __restrict__ P = s.params + s.pset[s.shard_begin + i];
+  const DevParams* __restrict__ P = s.params + pset;
   const int nm                    = NM_T > 0 ? NM_T : P->n_motors;
   const int mode0                 = MODE_T >= 0 ? MODE_T : int(s.mode[i]);
-  uint32_t  flags                 = s.flags[i];
+  uint32_t flags                  = flags0;
 
-#define LD(arr, row) (arr)[int64_t(row) * ld + i]
-#define ST(arr, row, val) (arr)[int64_t(row) * ld + i] = (val)
+#define LD(tp, row) (tp)[(row) * MRSB_TILE]
+#define ST(tp, row, val)                         \
+  do {                                           \
+    if (valid) (tp)[(row) * MRSB_TILE] = (val);  \
+  } while (0)
 
   // ---- load state -------------------------------------------------------------------------
-  Vec3 x = mk(LD(s.st, 0), LD(s.st, 1), LD(s.st, 2));
-  Vec3 v = mk(LD(s.st, 3), LD(s.st, 4), LD(s.st, 5));
+  Vec3 x = mk(LD(t_st, 0), LD(t_st, 1), LD(t_st, 2));
+  Vec3 v = mk(LD(t_st, 3), LD(t_st, 4), LD(t_st, 5));
   Rot  R;
-  R.c0   = mk(LD(s.st, 6), LD(s.st, 7), LD(s.st, 8));
-  R.c1   = mk(LD(s.st, 9), LD(s.st, 10), LD(s.st, 11));
-  R.c2   = mk(LD(s.st, 12), LD(s.st, 13), LD(s.st, 14));
-  Vec3 w = mk(LD(s.st, 15), LD(s.st, 16), LD(s.st, 17));
+  R.c0   = mk(LD(t_st, 6), LD(t_st, 7), LD(t_st, 8));
+  R.c1   = mk(LD(t_st, 9), LD(t_st, 10), LD(t_st, 11));
+  R.c2   = mk(LD(t_st, 12), LD(t_st, 13), LD(t_st, 14));
+  Vec3 w = mk(LD(t_st, 15), LD(t_st, 16), LD(t_st, 17));
   double rpm[MRSB_NM];
 #pragma unroll
-  for (int m = 0; m < MRSB_NM; m++) rpm[m] = (m < nm) ? LD(s.rpm, m) : 0.0;
+  for (int m = 0; m < MRSB_NM; m++) rpm[m] = (m < nm) ? LD(t_rpm, m) : 0.0;
   Vec3 vprev = v;
-  if (flags & FLAG_VPREV) vprev = mk(LD(s.vprev, 0), LD(s.vprev, 1), LD(s.vprev, 2));
-  const Vec3 fext = mk(LD(s.fext, 0), LD(s.fext, 1), LD(s.fext, 2));
+  if (flags & FLAG_VPREV) vprev = mk(LD(t_vprev, 0), LD(t_vprev, 1), LD(t_vprev, 2));
+  const Vec3 fext = mk(LD(t_fext, 0), LD(t_fext, 1), LD(t_fext, 2));
   Vec3       mext = mk(0, 0, 0);
-  if (any_moment) mext = mk(LD(s.mext, 0), LD(s.mext, 1), LD(s.mext, 2));
+  if (any_moment) mext = mk(LD(t_mext, 0), LD(t_mext, 1), LD(t_mext, 2));
 
   const bool live = !(flags & FLAG_CRASHED) && mode0 != MRSB_INPUT_UNKNOWN;  // US:308
   // which controllers are on this UAV's path (decides which PID rows are touched)
@@ -207,13 +385,13 @@ __global__ void __launch_bounds__(MRSB_STEP_THREADS, MRSB_STEP_MINB) uav_step_ke
 
   double pd[PID_ROWS];
 #pragma unroll
-  for (int r = 0; r < 6; r++) pd[r] = on_pos ? LD(s.pid, r) : 0.0;
+  for (int r = 0; r < 6; r++) pd[r] = on_pos ? LD(t_pid, r) : 0.0;
 #pragma unroll
-  for (int r = 6; r < 12; r++) pd[r] = on_vel ? LD(s.pid, r) : 0.0;
+  for (int r = 6; r < 12; r++) pd[r] = on_vel ? LD(t_pid, r) : 0.0;
 #pragma unroll
-  for (int r = 12; r < 18; r++) pd[r] = on_att ? LD(s.pid, r) : 0.0;
+  for (int r = 12; r < 18; r++) pd[r] = on_att ? LD(t_pid, r) : 0.0;
 #pragma unroll
-  for (int r = 18; r < 24; r++) pd[r] = on_rate ? LD(s.pid, r) : 0.0;
+  for (int r = 18; r < 24; r++) pd[r] = on_rate ? LD(t_pid, r) : 0.0;
 
   // command payload
   double c[CMD_ROWS];
@@ -223,17 +401,17 @@ __global__ void __launch_bounds__(MRSB_STEP_THREADS, MRSB_STEP_MINB) uav_step_ke
     if (mode0 == MRSB_ACTUATOR_CMD) {
 #pragma unroll
       for (int m = 0; m < MRSB_NM; m++)
-        if (m < nm) c[m] = LD(s.cmd, m);
+        if (m < nm) c[m] = LD(t_cmd, m);
     } else if (mode0 == MRSB_ATTITUDE_CMD) {
 #pragma unroll
-      for (int r = 0; r < 10; r++) c[r] = LD(s.cmd, r);
+      for (int r = 0; r < 10; r++) c[r] = LD(t_cmd, r);
     } else {
 #pragma unroll
-      for (int r = 0; r < 4; r++) c[r] = LD(s.cmd, r);
-      if (mode0 == MRSB_TILT_HDG_RATE_CMD) c[4] = LD(s.cmd, 4);
+      for (int r = 0; r < 4; r++) c[r] = LD(t_cmd, r);
+      if (mode0 == MRSB_TILT_HDG_RATE_CMD) c[4] = LD(t_cmd, 4);
       if (mode0 == MRSB_POSITION_CMD || mode0 == MRSB_VELOCITY_HDG_CMD || mode0 == MRSB_ACCELERATION_HDG_CMD) {
-        c[CMD_COS] = LD(s.cmd, CMD_COS);
-        c[CMD_SIN] = LD(s.cmd, CMD_SIN);
+        c[CMD_COS] = LD(t_cmd, CMD_COS);
+        c[CMD_SIN] = LD(t_cmd, CMD_SIN);
       }
     }
   }
@@ -242,9 +420,9 @@ __global__ void __launch_bounds__(MRSB_STEP_THREADS, MRSB_STEP_MINB) uav_step_ke
   double ff_hdg_rate = 0.0;
   if (on_pos) {
     if (flags & FLAG_FF_VEL_HDG) {
-      ff_vel = mk(LD(s.ff, FF_VEL_HDG + 0), LD(s.ff, FF_VEL_HDG + 1), LD(s.ff, FF_VEL_HDG + 2));
+      ff_vel = mk(LD(t_ff, FF_VEL_HDG + 0), LD(t_ff, FF_VEL_HDG + 1), LD(t_ff, FF_VEL_HDG + 2));
     } else if (flags & FLAG_FF_VEL_HDG_RATE) {
-      ff_vel = mk(LD(s.ff, FF_VEL_HDG_RATE + 0), LD(s.ff, FF_VEL_HDG_RATE + 1), LD(s.ff, FF_VEL_HDG_RATE + 2));
+      ff_vel = mk(LD(t_ff, FF_VEL_HDG_RATE + 0), LD(t_ff, FF_VEL_HDG_RATE + 1), LD(t_ff, FF_VEL_HDG_RATE + 2));
     }
   }
   if (on_vel) {
@@ -254,13 +432,15 @@ __global__ void __launch_bounds__(MRSB_STEP_THREADS, MRSB_STEP_MINB) uav_step_ke
     // hdg branch: acc_hdg first, else acc_hdg_rate (US:330-334); rate branch: acc_hdg_rate first (+heading_rate), else acc_hdg (US:341-346)
     const bool use_ar = hdg_branch ? (!has_a && has_ar) : has_ar;
     const bool use_a  = hdg_branch ? has_a : (!has_ar && has_a);
-    if (use_a) ff_acc = mk(LD(s.ff, FF_ACC_HDG + 0), LD(s.ff, FF_ACC_HDG + 1), LD(s.ff, FF_ACC_HDG + 2));
+    if (use_a) ff_acc = mk(LD(t_ff, FF_ACC_HDG + 0), LD(t_ff, FF_ACC_HDG + 1), LD(t_ff, FF_ACC_HDG + 2));
     if (use_ar) {
-      ff_acc = mk(LD(s.ff, FF_ACC_HDG_RATE + 0), LD(s.ff, FF_ACC_HDG_RATE + 1), LD(s.ff, FF_ACC_HDG_RATE + 2));
-      if (!hdg_branch) ff_hdg_rate = LD(s.ff, FF_ACC_HDG_RATE + 3);
+      ff_acc = mk(LD(t_ff, FF_ACC_HDG_RATE + 0), LD(t_ff, FF_ACC_HDG_RATE + 1), LD(t_ff, FF_ACC_HDG_RATE + 2));
+      if (!hdg_branch) ff_hdg_rate = LD(t_ff, FF_ACC_HDG_RATE + 3);
     }
   }
   const double initz = (flags & FLAG_TAKEOFF) ? s.initz[i] : 0.0;
+
+  after_loads();  // nothing below reads through `in`
 
   // ---- per-launch constants ---------------------------------------------------------------
   const double inv_dt   = 1.0 / dt;
@@ -271,6 +451,7 @@ __global__ void __launch_bounds__(MRSB_STEP_THREADS, MRSB_STEP_MINB) uav_step_ke
   const Vec3   Jd       = mk(P->J[0], P->J[4], P->J[8]);
   const Vec3   Jdi      = mk(P->Jinv[0], P->Jinv[4], P->Jinv[8]);
   const double min_rpm = P->min_rpm, rpm_range = P->rpm_range;
+  const double inv_nm  = 1.0 / double(nm);
 
   Vec3 imu = mk(0, 0, 0);
 
@@ -312,11 +493,11 @@ __global__ void __launch_bounds__(MRSB_STEP_THREADS, MRSB_STEP_MINB) uav_step_ke
         const Vec3   fd   = mk(vec.x * mass, vec.y * mass, (vec.z + g) * mass);
         const Vec3   n    = normalized(fd);
         const double tf   = dot(fd, R.c2);
-        throttle          = (sqrt(tf / P->kf_n) - min_rpm) * P->inv_rpm_range;
+        throttle          = (sqrt_fast(tf * P->inv_kf_n) - min_rpm) * P->inv_rpm_range;
         if (mode == MRSB_ACCELERATION_HDG_CMD) {
           const double ch = c[CMD_COS], sh = c[CMD_SIN];
           const double num = n.x * ch + n.y * sh;
-          const double z3  = (num == 0.0) ? 0.0 : -num / n.z;
+          const double z3  = (num == 0.0) ? 0.0 : -num * rcp_fast(n.z);
           Rd.c2            = n;
           Rd.c0            = normalized(mk(ch, sh, z3));
           Rd.c1            = normalized(cross(Rd.c2, Rd.c0));
@@ -354,7 +535,10 @@ __global__ void __launch_bounds__(MRSB_STEP_THREADS, MRSB_STEP_MINB) uav_step_ke
           const double hx = R.c0.x, hy = R.c0.y;
           const double den = hx * hx + hy * hy;
           double       parasitic = 0.0;
-          if (!(fabs(den) <= 1e-5)) parasitic = (-hy / den) * rd00 + (hx / den) * rd10;
+          if (!(fabs(den) <= 1e-5)) {
+            const double iden = rcp_fast(den);
+            parasitic         = (-hy * iden) * rd00 + (hx * iden) * rd10;
+          }
           // getYawRateIntrinsic (:212-251)
           const double hr  = sc - parasitic;
           double       yaw = 0.0;
@@ -363,9 +547,9 @@ __global__ void __launch_bounds__(MRSB_STEP_THREADS, MRSB_STEP_MINB) uav_step_ke
             const Vec3   b    = normalized(mk(-hy, hx, 0.0));
             const double bp   = b.x * R.c1.x + (b.y * R.c1.y + b.z * R.c1.z);
             const Vec3   proj = b * bp;
-            const double on = sqrt(dot(orb, orb)), pn = sqrt(dot(proj, proj));
+            const double on = sqrt_fast(dot(orb, orb)), pn = sqrt_fast(dot(proj, proj));
             if (!(fabs(pn) < 1e-5)) {
-              const double o = double(signum(dot(orb, proj))) * (on / pn);
+              const double o = double(signum(dot(orb, proj))) * (on * rcp_fast(pn));
               yaw            = isfinite(o) ? o : 0.0;
             }
           }
@@ -406,15 +590,16 @@ __global__ void __launch_bounds__(MRSB_STEP_THREADS, MRSB_STEP_MINB) uav_step_ke
             }
           if (mx > 1.0) {
             if (throttle > 1e-2) {
-              const double sc2 = (sum / double(nm)) / throttle;
-              const double r0 = vec.x / sc2, r1 = vec.y / sc2, r2 = vec.z / sc2;
+              const double isc = throttle * rcp_fast(sum * inv_nm);  // 1 / (mean(m) / throttle)
+              const double r0 = vec.x * isc, r1 = vec.y * isc, r2 = vec.z * isc;
 #pragma unroll
               for (int m = 0; m < MRSB_NM; m++)
                 if (m < nm) u[m] = (P->mix[m][0] * r0 + P->mix[m][1] * r1) + (P->mix[m][2] * r2 + P->mix[m][3] * throttle);
             } else {
+              const double imx = rcp_fast(mx);
 #pragma unroll
               for (int m = 0; m < MRSB_NM; m++)
-                if (m < nm) u[m] /= mx;
+                if (m < nm) u[m] *= imx;
             }
           }
         }
@@ -428,19 +613,19 @@ __global__ void __launch_bounds__(MRSB_STEP_THREADS, MRSB_STEP_MINB) uav_step_ke
     if (last) {  // controller state is final for this launch: store it now, not after the RK4 (register pressure)
       if (on_pos) {
 #pragma unroll
-        for (int r = 0; r < 6; r++) ST(s.pid, r, pd[r]);
+        for (int r = 0; r < 6; r++) ST(o_pid, r, pd[r]);
       }
       if (on_vel) {
 #pragma unroll
-        for (int r = 6; r < 12; r++) ST(s.pid, r, pd[r]);
+        for (int r = 6; r < 12; r++) ST(o_pid, r, pd[r]);
       }
       if (on_att) {
 #pragma unroll
-        for (int r = 12; r < 18; r++) ST(s.pid, r, pd[r]);
+        for (int r = 12; r < 18; r++) ST(o_pid, r, pd[r]);
       }
       if (on_rate) {
 #pragma unroll
-        for (int r = 18; r < 24; r++) ST(s.pid, r, pd[r]);
+        for (int r = 18; r < 24; r++) ST(o_pid, r, pd[r]);
       }
     }
 
@@ -466,7 +651,7 @@ __global__ void __launch_bounds__(MRSB_STEP_THREADS, MRSB_STEP_MINB) uav_step_ke
           t2 = fma(P->alloc[2][m], sq, t2);
           t3 = fma(P->alloc[3][m], sq, t3);
           rpm[m] = filt * rpm[m] + (1.0 - filt) * target;
-          if (last) ST(s.rpm, m, rpm[m]);
+          if (last) ST(o_rpm, m, rpm[m]);
         }
       }
       fz.g        = g;
@@ -476,65 +661,23 @@ __global__ void __launch_bounds__(MRSB_STEP_THREADS, MRSB_STEP_MINB) uav_step_ke
       fz.tau      = mk(t0, t1, t2) + mext;
     }
 
-    // classic RK4, running weighted sum
-    const double h = 0.5 * dt;
-    Slope        k = derivative(v, R, w, fz, P, jdiag, Jd, Jdi);
-    Vec3         sx = v, sv = k.dv, sw = k.dw;
-    Rot          sR = k.dR;
-    Vec3         vt = fma3(k.dv, h, v), wt = fma3(k.dw, h, w);
-    Rot          Rt;
-    Rt.c0 = fma3(k.dR.c0, h, R.c0);
-    Rt.c1 = fma3(k.dR.c1, h, R.c1);
-    Rt.c2 = fma3(k.dR.c2, h, R.c2);
-
-    k  = derivative(vt, Rt, wt, fz, P, jdiag, Jd, Jdi);
-    sx = fma3(vt, 2.0, sx);
-    sv = fma3(k.dv, 2.0, sv);
-    sw = fma3(k.dw, 2.0, sw);
-    sR.c0 = fma3(k.dR.c0, 2.0, sR.c0);
-    sR.c1 = fma3(k.dR.c1, 2.0, sR.c1);
-    sR.c2 = fma3(k.dR.c2, 2.0, sR.c2);
-    vt    = fma3(k.dv, h, v);
-    wt    = fma3(k.dw, h, w);
-    Rt.c0 = fma3(k.dR.c0, h, R.c0);
-    Rt.c1 = fma3(k.dR.c1, h, R.c1);
-    Rt.c2 = fma3(k.dR.c2, h, R.c2);
-
-    k  = derivative(vt, Rt, wt, fz, P, jdiag, Jd, Jdi);
-    sx = fma3(vt, 2.0, sx);
-    sv = fma3(k.dv, 2.0, sv);
-    sw = fma3(k.dw, 2.0, sw);
-    sR.c0 = fma3(k.dR.c0, 2.0, sR.c0);
-    sR.c1 = fma3(k.dR.c1, 2.0, sR.c1);
-    sR.c2 = fma3(k.dR.c2, 2.0, sR.c2);
-    vt    = fma3(k.dv, dt, v);
-    wt    = fma3(k.dw, dt, w);
-    Rt.c0 = fma3(k.dR.c0, dt, R.c0);
-    Rt.c1 = fma3(k.dR.c1, dt, R.c1);
-    Rt.c2 = fma3(k.dR.c2, dt, R.c2);
-
-    k  = derivative(vt, Rt, wt, fz, P, jdiag, Jd, Jdi);
-    sx = sx + vt;
-    sv = sv + k.dv;
-    sw = sw + k.dw;
-    sR.c0 = sR.c0 + k.dR.c0;
-    sR.c1 = sR.c1 + k.dR.c1;
-    sR.c2 = sR.c2 + k.dR.c2;
-
-    const double h6 = dt * (1.0 / 6.0);
-    const Vec3   xn = fma3(sx, h6, x), vn = fma3(sv, h6, v), wn = fma3(sw, h6, w);
-    Rot          Rn;
-    Rn.c0 = fma3(sR.c0, h6, R.c0);
-    Rn.c1 = fma3(sR.c1, h6, R.c1);
-    Rn.c2 = fma3(sR.c2, h6, R.c2);
+    // classic RK4
+    Rigid cur, nxt;
+    cur.x = x;
+    cur.v = v;
+    cur.w = w;
+    cur.R = R;
+    rk4<false>(cur, nxt, dt, fz, P, jdiag, Jd, Jdi);
 
     // MM:228-233: any NaN -> keep the pre-step state
-    const bool bad = isnan3(xn) | isnan3(vn) | isnan3(wn) | isnan3(Rn.c0) | isnan3(Rn.c1) | isnan3(Rn.c2);
+    bool bad = false;
+    if (max(max(expo3(nxt.x), expo3(nxt.v)), max(max(expo3(nxt.w), expo3(nxt.R.c0)), max(expo3(nxt.R.c1), expo3(nxt.R.c2)))) == 0x7ff00000u)
+      bad = isnan3(nxt.x) | isnan3(nxt.v) | isnan3(nxt.w) | isnan3(nxt.R.c0) | isnan3(nxt.R.c1) | isnan3(nxt.R.c2);
     if (!bad) {
-      x = xn;
-      v = vn;
-      w = wn;
-      R = Rn;
+      x = nxt.x;
+      v = nxt.v;
+      w = nxt.w;
+      R = nxt.R;
     }
 
     R = reortho(R);  // MM:249-253
@@ -547,7 +690,7 @@ __global__ void __launch_bounds__(MRSB_STEP_THREADS, MRSB_STEP_MINB) uav_step_ke
       }
     }
     if (flags & FLAG_TAKEOFF) {  // MM:264-277
-      if (usum / double(nm) <= P->takeoff_rpm) {
+      if (usum * inv_nm <= P->takeoff_rpm) {
         if (x.z < initz && v.z < 0.0) {
           x.z = initz;
           v   = mk(0, 0, 0);
@@ -565,36 +708,119 @@ __global__ void __launch_bounds__(MRSB_STEP_THREADS, MRSB_STEP_MINB) uav_step_ke
   }
 
   // ---- store ------------------------------------------------------------------------------
-  ST(s.st, 0, x.x);
-  ST(s.st, 1, x.y);
-  ST(s.st, 2, x.z);
-  ST(s.st, 3, v.x);
-  ST(s.st, 4, v.y);
-  ST(s.st, 5, v.z);
-  ST(s.st, 6, R.c0.x);
-  ST(s.st, 7, R.c0.y);
-  ST(s.st, 8, R.c0.z);
-  ST(s.st, 9, R.c1.x);
-  ST(s.st, 10, R.c1.y);
-  ST(s.st, 11, R.c1.z);
-  ST(s.st, 12, R.c2.x);
-  ST(s.st, 13, R.c2.y);
-  ST(s.st, 14, R.c2.z);
-  ST(s.st, 15, w.x);
-  ST(s.st, 16, w.y);
-  ST(s.st, 17, w.z);
-  ST(s.imu, 0, imu.x);
-  ST(s.imu, 1, imu.y);
-  ST(s.imu, 2, imu.z);
+  ST(o_st, 0, x.x);
+  ST(o_st, 1, x.y);
+  ST(o_st, 2, x.z);
+  ST(o_st, 3, v.x);
+  ST(o_st, 4, v.y);
+  ST(o_st, 5, v.z);
+  ST(o_st, 6, R.c0.x);
+  ST(o_st, 7, R.c0.y);
+  ST(o_st, 8, R.c0.z);
+  ST(o_st, 9, R.c1.x);
+  ST(o_st, 10, R.c1.y);
+  ST(o_st, 11, R.c1.z);
+  ST(o_st, 12, R.c2.x);
+  ST(o_st, 13, R.c2.y);
+  ST(o_st, 14, R.c2.z);
+  ST(o_st, 15, w.x);
+  ST(o_st, 16, w.y);
+  ST(o_st, 17, w.z);
+  ST(o_imu, 0, imu.x);
+  ST(o_imu, 1, imu.y);
+  ST(o_imu, 2, imu.z);
   const uint32_t new_flags = flags & ~FLAG_VPREV;
-  if (new_flags != s.flags[i]) s.flags[i] = new_flags;
-  // packed position for the collision pass / the cross-shard all-gather
-  double* gp = s.gpos + 3 * (s.shard_begin + i);
-  gp[0]      = x.x;
-  gp[1]      = x.y;
-  gp[2]      = x.z;
+  if (valid) {
+    if (new_flags != flags0) s.flags[i] = new_flags;
+    // packed position for the collision pass / the cross-shard all-gather
+    double* gp = s.gpos + 3 * (s.shard_begin + i);
+    gp[0]      = x.x;
+    gp[1]      = x.y;
+    gp[2]      = x.z;
+  }
 #undef LD
 #undef ST
+}
+
+// ---- direct kernel: one CTA per tile, inputs read straight from HBM ----------------------------
+template <int NM_T, int MODE_T, bool ONE>
+__global__ void __launch_bounds__(MRSB_STEP_THREADS, MRSB_STEP_MINB) uav_step_kernel(DevState s, double dt, int k_sub, int any_moment) {
+  const int64_t tile = blockIdx.x;
+  TileIn        in;
+  in.st   = s.st + (tile * ST_ROWS) * MRSB_TILE + threadIdx.x;
+  in.rpm  = s.rpm + (tile * MRSB_NM) * MRSB_TILE + threadIdx.x;
+  in.pid  = s.pid + (tile * PID_ROWS) * MRSB_TILE + threadIdx.x;
+  in.cmd  = s.cmd + (tile * CMD_ROWS) * MRSB_TILE + threadIdx.x;
+  in.fext = s.fext + (tile * F3_ROWS) * MRSB_TILE + threadIdx.x;
+  const int64_t i = min(tile * MRSB_TILE + threadIdx.x, s.n - 1);
+  step_uav<NM_T, MODE_T, ONE>(s, in, tile, s.flags[i], s.pset[s.shard_begin + i], dt, k_sub, any_moment, [] {});
+}
+
+// ---- staged kernel: persistent CTAs, the NEXT tile's inputs are fetched by the TMA unit into
+// shared memory while the current tile is being integrated out of registers ----------------------
+// shared-memory tile image (rows of 128 doubles): st 18 | rpm 8 | pid 24 | cmd 12 | fext 3
+#define SM_ST 0
+#define SM_RPM (SM_ST + ST_ROWS)
+#define SM_PID (SM_RPM + MRSB_NM)
+#define SM_CMD (SM_PID + PID_ROWS)
+#define SM_FEXT (SM_CMD + CMD_ROWS)
+#define SM_ROWS (SM_FEXT + F3_ROWS)
+
+template <int NM_T, int MODE_T>
+DEV void stage_tile(const DevState& s, double* sm, uint64_t* bar, int64_t tile) {
+  static_assert(MODE_T >= 0 && NM_T > 0, "the staged kernel is for batches with a uniform input mode and motor count");
+  constexpr int      kRow      = MRSB_TILE * int(sizeof(double));
+  constexpr int      pid_lo    = MODE_T == MRSB_POSITION_CMD ? 0 : MODE_T >= MRSB_VELOCITY_HDG_RATE_CMD ? 6 : MODE_T >= MRSB_ATTITUDE_CMD ? 12 : MODE_T >= MRSB_ATTITUDE_RATE_CMD ? 18 : 24;
+  constexpr int      cmd_rows  = MODE_T == MRSB_ACTUATOR_CMD ? NM_T : MODE_T == MRSB_ATTITUDE_CMD ? 10 : MODE_T == MRSB_TILT_HDG_RATE_CMD ? 5 : 4;
+  constexpr bool     hdg       = MODE_T == MRSB_POSITION_CMD || MODE_T == MRSB_VELOCITY_HDG_CMD || MODE_T == MRSB_ACCELERATION_HDG_CMD;
+  constexpr uint32_t bytes     = uint32_t(kRow) * (ST_ROWS + NM_T + (PID_ROWS - pid_lo) + cmd_rows + (hdg ? 2 : 0) + F3_ROWS);
+  mbar_expect_tx(bar, bytes);
+  tma_load(sm + SM_ST * MRSB_TILE, s.st + (tile * ST_ROWS) * MRSB_TILE, kRow * ST_ROWS, bar);
+  tma_load(sm + SM_RPM * MRSB_TILE, s.rpm + (tile * MRSB_NM) * MRSB_TILE, kRow * NM_T, bar);
+  if (pid_lo < PID_ROWS)
+    tma_load(sm + (SM_PID + pid_lo) * MRSB_TILE, s.pid + (tile * PID_ROWS + pid_lo) * MRSB_TILE, kRow * (PID_ROWS - pid_lo), bar);
+  tma_load(sm + SM_CMD * MRSB_TILE, s.cmd + (tile * CMD_ROWS) * MRSB_TILE, kRow * cmd_rows, bar);
+  if (hdg) tma_load(sm + (SM_CMD + CMD_COS) * MRSB_TILE, s.cmd + (tile * CMD_ROWS + CMD_COS) * MRSB_TILE, kRow * 2, bar);
+  tma_load(sm + SM_FEXT * MRSB_TILE, s.fext + (tile * F3_ROWS) * MRSB_TILE, kRow * F3_ROWS, bar);
+}
+
+template <int NM_T, int MODE_T, bool ONE>
+__global__ void __launch_bounds__(MRSB_STEP_THREADS, MRSB_STEP_MINB) uav_step_staged_kernel(DevState s, double dt, int k_sub, int any_moment, int64_t n_tiles) {
+  extern __shared__ __align__(128) double sm[];  // SM_ROWS x 128 doubles
+  __shared__ uint64_t bar;
+  if (threadIdx.x == 0) mbar_init(&bar, 1);
+  __syncthreads();
+  int64_t tile = blockIdx.x;
+  if (threadIdx.x == 0 && tile < n_tiles) stage_tile<NM_T, MODE_T>(s, sm, &bar, tile);
+  TileIn in;
+  in.st   = sm + SM_ST * MRSB_TILE + threadIdx.x;
+  in.rpm  = sm + SM_RPM * MRSB_TILE + threadIdx.x;
+  in.pid  = sm + SM_PID * MRSB_TILE + threadIdx.x;
+  in.cmd  = sm + SM_CMD * MRSB_TILE + threadIdx.x;
+  in.fext = sm + SM_FEXT * MRSB_TILE + threadIdx.x;
+  uint32_t phase = 0;
+  // the two per-UAV words that are not part of the tile image are prefetched one tile ahead
+  int64_t  i0        = min(tile * MRSB_TILE + threadIdx.x, s.n - 1);
+  uint32_t flags_cur = tile < n_tiles ? s.flags[i0] : 0u;
+  int32_t  pset_cur  = tile < n_tiles ? s.pset[s.shard_begin + i0] : 0;
+  for (; tile < n_tiles; tile += gridDim.x) {
+    const int64_t next = tile + gridDim.x;
+    uint32_t      flags_next = 0u;
+    int32_t       pset_next  = 0;
+    if (next < n_tiles) {
+      const int64_t in_ = min(next * MRSB_TILE + threadIdx.x, s.n - 1);
+      flags_next        = s.flags[in_];
+      pset_next         = s.pset[s.shard_begin + in_];
+    }
+    mbar_wait(&bar, phase);
+    phase ^= 1u;
+    step_uav<NM_T, MODE_T, ONE>(s, in, tile, flags_cur, pset_cur, dt, k_sub, any_moment, [&] {
+      __syncthreads();  // every lane has its inputs in registers: the image may be overwritten
+      if (threadIdx.x == 0 && next < n_tiles) stage_tile<NM_T, MODE_T>(s, sm, &bar, next);
+    });
+    flags_cur = flags_next;
+    pset_cur  = pset_next;
+  }
 }
 
 __global__ void publish_positions_kernel(DevState s) {
@@ -606,14 +832,48 @@ __global__ void publish_positions_kernel(DevState s) {
   gp[2]      = s.st[2 * s.ld + i];
 }
 
+// CTAs of the staged kernel that fit on the device (persistent grid), cached per instantiation
+template <int NM_T, int MODE_T, bool ONE>
+int staged_grid(size_t smem) {
+  static int cached = -1;
+  if (cached < 0) {
+    auto* k = uav_step_staged_kernel<NM_T, MODE_T, ONE>;
+    if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess) {
+      cudaGetLastError();
+      cached = 0;
+      return cached;
+    }
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, MRSB_STEP_THREADS, smem);
+    cached = sms * per_sm;
+  }
+  return cached;
+}
+
 template <int NM_T, int MODE_T>
 void launch_one(const DevState& s, double dt, int k, int any_moment, cudaStream_t st) {
-  const int      threads = MRSB_STEP_THREADS;
-  const unsigned blocks  = unsigned((s.n + threads - 1) / threads);
+  const int     threads = MRSB_STEP_THREADS;
+  const int64_t n_tiles = (s.n + threads - 1) / threads;
+  if constexpr (NM_T > 0 && MODE_T >= 0) {
+    // enough tiles to fill the machine more than once: persistent CTAs + TMA staging hide the HBM
+    // latency behind the integration of the previous tile
+    const size_t smem = size_t(SM_ROWS) * MRSB_TILE * sizeof(double);
+    const int    grid = (k == 1) ? staged_grid<NM_T, MODE_T, true>(smem) : staged_grid<NM_T, MODE_T, false>(smem);
+    if (grid > 0 && n_tiles > grid && !getenv("MRSB_NO_STAGING")) {
+      if (k == 1) {
+        uav_step_staged_kernel<NM_T, MODE_T, true><<<grid, threads, smem, st>>>(s, dt, k, any_moment, n_tiles);
+      } else {
+        uav_step_staged_kernel<NM_T, MODE_T, false><<<grid, threads, smem, st>>>(s, dt, k, any_moment, n_tiles);
+      }
+      return;
+    }
+  }
   if (k == 1) {
-    uav_step_kernel<NM_T, MODE_T, true><<<blocks, threads, 0, st>>>(s, dt, k, any_moment);
+    uav_step_kernel<NM_T, MODE_T, true><<<unsigned(n_tiles), threads, 0, st>>>(s, dt, k, any_moment);
   } else {
-    uav_step_kernel<NM_T, MODE_T, false><<<blocks, threads, 0, st>>>(s, dt, k, any_moment);
+    uav_step_kernel<NM_T, MODE_T, false><<<unsigned(n_tiles), threads, 0, st>>>(s, dt, k, any_moment);
   }
 }
 
