@@ -424,14 +424,14 @@ int mrsb_create(const mrsb_create_info* info, mrsb_handle* out) {
     g.n_buckets = 1u << bits;
     CREATE_RC(dalloc(&g.bucket, ng));
     CREATE_RC(dalloc(&g.rank, ng));
-    CREATE_RC(dalloc(&g.count, size_t(g.n_buckets) + 1));
-    CREATE_RC(dalloc(&g.begin, size_t(g.n_buckets) + 1));
+    CREATE_RC(dalloc(&g.count, size_t(g.n_buckets) + 2));  // + mirror of bucket 0 + sentinel
+    CREATE_RC(dalloc(&g.begin, size_t(g.n_buckets) + 2));
     CREATE_RC(dalloc(&g.aabb, 6));
-    CREATE_RC(dalloc(&g.rec, ng));
+    CREATE_RC(dalloc(&g.rec, 2 * ng));  // worst case: every UAV in bucket 0 and mirrored
     g.pair_cap = int64_t(std::max<size_t>(4096, 4 * size_t(std::max<int64_t>(s.n, 1))));
     CREATE_RC(dalloc(&g.pairs, 2 * size_t(g.pair_cap)));
     CREATE_RC(dalloc(&g.counters, 4));
-    h->cub_tmp_bytes = collide_tmp_bytes(int64_t(g.n_buckets) + 1);
+    h->cub_tmp_bytes = collide_tmp_bytes(int64_t(g.n_buckets) + 2);
     CREATE_CU(cudaMalloc(&h->cub_tmp, std::max<size_t>(h->cub_tmp_bytes, 16)));
   }
   h->shard_begin_of = {s.shard_begin};

@@ -13,6 +13,7 @@
 //   K2c  scan     begin = exclusive prefix sum of count (CUB DeviceScan).
 //   K2d  scatter  rec[begin[bucket] + rank] = {x, y, z, index}  (32-byte records: a candidate costs
 //                 exactly one DRAM sector).  This is a counting sort: no radix passes.
+//                 Bucket B mirrors bucket 0, so a row never straddles the end of the table.
 //   K3   collide  one thread per record; the search ball of radius sqrt(3) < 2 m around p touches at
 //                 most 2 cells per axis (interval [p-2, p+2] has the length of one 4 m cell), i.e.
 //                 <= 4 stencil rows (cy0..cy1 x cz0..cz1), each one contiguous range cx0..cx1; per
@@ -118,17 +119,23 @@ __global__ void __launch_bounds__(256) count_kernel(const double* __restrict__ g
   const uint32_t b = (row_hash(cell_of(y), cell_of(z)) + uint32_t(cell_of(x))) & mask;
   bucket[j]        = b;
   rank[j]          = atomicAdd(&count[b], 1u);
+  // bucket B = mask+1 mirrors bucket 0 (same records, same ranks), so that the two x-adjacent cells
+  // of a stencil row are ALWAYS adjacent buckets, also across the end of the table
+  if (b == 0u) atomicAdd(&count[mask + 1u], 1u);
 }
 
 __global__ void __launch_bounds__(256) scatter_kernel(const double* __restrict__ gpos, int64_t n, const uint32_t* __restrict__ bucket,
-                                                      const uint32_t* __restrict__ rank, const uint32_t* __restrict__ begin,
+                                                      const uint32_t* __restrict__ rank, const uint32_t* __restrict__ begin, uint32_t n_buckets,
                                                       double4* __restrict__ rec) {
   const int64_t j = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (j >= n) return;
   const uint32_t b = bucket[j];
   if (b == 0xFFFFFFFFu) return;
-  const double* q = gpos + 3 * j;
-  rec[begin[b] + rank[j]] = make_double4(q[0], q[1], q[2], __longlong_as_double((long long)j));
+  const double*  q = gpos + 3 * j;
+  const double4  r = make_double4(q[0], q[1], q[2], __longlong_as_double((long long)j));
+  const uint32_t k = rank[j];
+  rec[begin[b] + k] = r;
+  if (b == 0u) rec[begin[n_buckets] + k] = r;  // mirror of bucket 0
 }
 
 // nanoflann L2 metric for dim 3, no contraction
@@ -140,145 +147,131 @@ DEV double nf_dist2(double ax, double ay, double az, double bx, double by, doubl
   return r;
 }
 
-struct Probe {
-  uint32_t lo, hi;  // record range
-  int      cy, cz;  // the stencil row this probe stands for
-};
-
-// the <= 4 stencil rows around q, each one contiguous record range cx0..cx1 (two ranges in the 1-in-B case of a table wrap)
-DEV int make_probes(const DevGrid& g, const double4& q, Probe pr[8]) {
-  const uint32_t mask = g.n_buckets - 1;
-  const int      cx0 = cell_of(q.x - kReach), cx1 = cell_of(q.x + kReach);
-  const int      cy0 = cell_of(q.y - kReach), cy1 = cell_of(q.y + kReach);
-  const int      cz0 = cell_of(q.z - kReach), cz1 = cell_of(q.z + kReach);
-  int            n   = 0;
-  for (int cz = cz0; cz <= cz1; cz++) {
-    for (int cy = cy0; cy <= cy1; cy++) {
-      const uint32_t b0 = (row_hash(cy, cz) + uint32_t(cx0)) & mask;
-      const uint32_t w  = uint32_t(cx1 - cx0);  // 0 or 1
-      pr[n].cy          = cy;
-      pr[n].cz          = cz;
-      if (b0 + w <= mask) {
-        pr[n].lo = g.begin[b0];
-        pr[n].hi = g.begin[b0 + w + 1];
-        n++;
-      } else {  // the two x cells straddle the end of the bucket table: two ranges for this row
-        pr[n].lo = g.begin[b0];
-        pr[n].hi = g.begin[b0 + 1];
-        n++;
-        pr[n].cy = cy;
-        pr[n].cz = cz;
-        pr[n].lo = g.begin[0];
-        pr[n].hi = g.begin[1];
-        n++;
-      }
-    }
-  }
-  return n;
-}
-
 __global__ void __launch_bounds__(128) collide_kernel(DevState s, DevGrid g, int crash_mode, double rebounce) {
   const int64_t p = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (p >= int64_t(g.begin[g.n_buckets])) return;
+  if (p >= int64_t(g.begin[g.n_buckets])) return;  // beyond the primary records (the mirror bucket holds copies)
   const double4 q  = g.rec[p];
   const int64_t gi = __double_as_longlong(q.w);
   const int64_t li = gi - s.shard_begin;
   if (li < 0 || li >= s.n) return;  // halo record: its owner handles it
 
-  const DevParams* __restrict__ Pi = s.params + s.pset[gi];
-  const double ai = Pi->arm_length, pi_ = Pi->prop_radius, mi = Pi->mass;
-  const double api = __dadd_rn(ai, pi_);
-
-  Probe     pr[8];
-  const int n_probes = make_probes(g, q, pr);
-
-  int    hits       = 0;
-  bool   crashed_me = false;
-  double fx = 0.0, fy = 0.0, fz = 0.0;
-
-  auto contribution = [&](const double4& r, const DevParams* __restrict__ Pj, double& cx_, double& cy_, double& cz_) {
-    // rebounce * normalized(x_i - x_j) * m_i * (m_j / (m_i + m_j))   (SIM:350), Eigen evaluation order
-    const double rx = __dsub_rn(q.x, r.x), ry = __dsub_rn(q.y, r.y), rz = __dsub_rn(q.z, r.z);
-    const double z  = __dadd_rn(__dmul_rn(rx, rx), __dadd_rn(__dmul_rn(ry, ry), __dmul_rn(rz, rz)));
-    double       nx = rx, ny = ry, nz = rz;
-    if (z > 0.0) {
-      const double sq = __dsqrt_rn(z);
-      nx              = __ddiv_rn(rx, sq);
-      ny              = __ddiv_rn(ry, sq);
-      nz              = __ddiv_rn(rz, sq);
+  // the <= 4 stencil rows (cy0..cy1) x (cz0..cz1) around q; each is ONE record range cx0..cx1
+  const uint32_t mask = g.n_buckets - 1;
+  const int      cx0 = cell_of(q.x - kReach), cx1 = cell_of(q.x + kReach);
+  const int      cy0 = cell_of(q.y - kReach), cy1 = cell_of(q.y + kReach);
+  const int      cz0 = cell_of(q.z - kReach), cz1 = cell_of(q.z + kReach);
+  const uint32_t w   = uint32_t(cx1 - cx0) + 1u;  // 1 or 2 buckets
+  int            rcy[4], rcz[4];
+  uint32_t       lo[4], hi[4];
+  double4        first[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    rcy[k]        = (k & 1) ? cy1 : cy0;
+    rcz[k]        = (k & 2) ? cz1 : cz0;
+    const bool on = (!(k & 1) || cy1 != cy0) && (!(k & 2) || cz1 != cz0);
+    lo[k] = hi[k] = 0u;
+    if (on) {
+      const uint32_t b0 = (row_hash(rcy[k], rcz[k]) + uint32_t(cx0)) & mask;
+      lo[k]             = g.begin[b0];
+      hi[k]             = g.begin[b0 + w];  // b0 + w <= mask + 2: begin[] has the mirror bucket and a sentinel
     }
-    const double mj = Pj->mass;
-    const double wt = __ddiv_rn(mj, __dadd_rn(mi, mj));
-    cx_             = __dmul_rn(__dmul_rn(__dmul_rn(rebounce, nx), mi), wt);
-    cy_             = __dmul_rn(__dmul_rn(__dmul_rn(rebounce, ny), mi), wt);
-    cz_             = __dmul_rn(__dmul_rn(__dmul_rn(rebounce, nz), mi), wt);
-  };
+  }
+#pragma unroll
+  for (int k = 0; k < 4; k++) first[k] = lo[k] < hi[k] ? g.rec[lo[k]] : q;  // the four leading candidates are fetched together
 
-  // a record r found in probe k is a genuine, not-yet-seen neighbour candidate iff it lies in the
-  // search ball AND its own cell row is the probe's row (rejects bucket aliases and duplicates)
-  auto in_ball = [&](const double4& r, const Probe& k, double& d2) {
-    d2 = nf_dist2(q.x, q.y, q.z, r.x, r.y, r.z);
+  // ---- phase 1 (cheap, unrolled): which records are in the search ball?  A record r found in row k
+  // is a genuine, not-yet-seen neighbour iff d2 < 3.0 AND its own cell row is row k (rejects bucket
+  // aliases and duplicates).  Almost every UAV has none; keep the first two, count the rest.
+  auto in_ball = [&](const double4& r, int k) {
+    if (__double_as_longlong(r.w) == gi) return false;  // SIM:335
+    const double d2 = nf_dist2(q.x, q.y, q.z, r.x, r.y, r.z);
     if (!(d2 < 3.0)) return false;  // NF:305-309
-    return cell_of(r.y) == k.cy && cell_of(r.z) == k.cz;
+    return cell_of(r.y) == rcy[k] && cell_of(r.z) == rcz[k];
   };
+  int      n_ball = 0;
+  uint32_t h0 = 0, h1 = 0;
+  auto     note = [&](uint32_t t) {
+    if (n_ball == 0) h0 = t;
+    if (n_ball == 1) h1 = t;
+    n_ball++;
+  };
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    if (lo[k] < hi[k]) {
+      if (in_ball(first[k], k)) note(lo[k]);
+      for (uint32_t t = lo[k] + 1; t < hi[k]; t++)
+        if (in_ball(g.rec[t], k)) note(t);
+    }
+  }
 
-  for (int k = 0; k < n_probes; k++) {
-    for (uint32_t t = pr[k].lo; t < pr[k].hi; t++) {
-      const double4 r  = g.rec[t];
+  double fx = 0.0, fy = 0.0, fz = 0.0;
+  bool   crashed_me = false;
+  if (n_ball > 0) {
+    // ---- phase 2 (rare, one copy of the heavy code): thresholds, pair list, force, crash flag
+    const DevParams* __restrict__ Pi = s.params + s.pset[gi];
+    const double ai = Pi->arm_length, pi_ = Pi->prop_radius, mi = Pi->mass;
+    const double api = __dadd_rn(ai, pi_);
+    auto process = [&](const double4& r) {
       const int64_t gj = __double_as_longlong(r.w);
-      double        d2;
-      if (gj == gi || !in_ball(r, pr[k], d2)) continue;  // SIM:335
+      const double  d2 = nf_dist2(q.x, q.y, q.z, r.x, r.y, r.z);
       const DevParams* __restrict__ Pj = s.params + s.pset[gj];
       const double aj = Pj->arm_length, pj = Pj->prop_radius;
       const double crit_ij = __dadd_rn(__dadd_rn(api, aj), pj);  // SIM:342
       if (d2 < crit_ij) {                                         // SIM:346
-        hits++;
         const unsigned long long slot = atomicAdd(g.counters, 1ull);
         if (slot < (unsigned long long)g.pair_cap) {
           g.pairs[2 * slot]     = int32_t(gi);
           g.pairs[2 * slot + 1] = int32_t(gj);
         }
         if (!crash_mode) {
-          double ax, ay, az;
-          contribution(r, Pj, ax, ay, az);
-          fx = __dadd_rn(fx, ax);
-          fy = __dadd_rn(fy, ay);
-          fz = __dadd_rn(fz, az);
+          // rebounce * normalized(x_i - x_j) * m_i * (m_j / (m_i + m_j))   (SIM:350), Eigen evaluation order
+          const double rx = __dsub_rn(q.x, r.x), ry = __dsub_rn(q.y, r.y), rz = __dsub_rn(q.z, r.z);
+          const double z  = __dadd_rn(__dmul_rn(rx, rx), __dadd_rn(__dmul_rn(ry, ry), __dmul_rn(rz, rz)));
+          double       nx = rx, ny = ry, nz = rz;
+          if (z > 0.0) {
+            const double sq = __dsqrt_rn(z);
+            nx              = __ddiv_rn(rx, sq);
+            ny              = __ddiv_rn(ry, sq);
+            nz              = __ddiv_rn(rz, sq);
+          }
+          const double mj = Pj->mass;
+          const double wt = __ddiv_rn(mj, __dadd_rn(mi, mj));
+          fx              = __dadd_rn(fx, __dmul_rn(__dmul_rn(__dmul_rn(rebounce, nx), mi), wt));
+          fy              = __dadd_rn(fy, __dmul_rn(__dmul_rn(__dmul_rn(rebounce, ny), mi), wt));
+          fz              = __dadd_rn(fz, __dmul_rn(__dmul_rn(__dmul_rn(rebounce, nz), mi), wt));
         }
       }
       if (crash_mode) {
         const double crit_ji = __dadd_rn(__dadd_rn(__dadd_rn(aj, pj), ai), pi_);  // threshold of the directed pair (j,i)
         if (d2 < crit_ji) crashed_me = true;
       }
-    }
-  }
-
-  if (!crash_mode && hits >= 3) {
-    // >= 3 simultaneous neighbours: redo the sum in ascending j so that the result does not depend
-    // on the arrival order inside the buckets (selection by repeated scan; such clusters are rare)
-    fx = fy = fz = 0.0;
-    int64_t last = -1;
-    for (int c = 0; c < hits; c++) {
-      int64_t best = INT64_MAX;
-      double  bx = 0, by = 0, bz = 0;
-      for (int k = 0; k < n_probes; k++) {
-        for (uint32_t t = pr[k].lo; t < pr[k].hi; t++) {
-          const double4 r  = g.rec[t];
-          const int64_t gj = __double_as_longlong(r.w);
-          double        d2;
-          if (gj == gi || gj <= last || gj >= best || !in_ball(r, pr[k], d2)) continue;
-          const DevParams* __restrict__ Pj = s.params + s.pset[gj];
-          if (d2 < __dadd_rn(__dadd_rn(api, Pj->arm_length), Pj->prop_radius)) {
+    };
+    if (n_ball <= 2) {
+      // sums of <= 2 terms do not depend on the order
+      for (int c = 0; c < n_ball; c++) {
+        process(g.rec[h0]);
+        h0 = h1;
+      }
+    } else {
+      // >= 3 neighbours in the ball: visit them in ascending j so that the force sum does not
+      // depend on the arrival order inside the buckets (selection by repeated scan; rare)
+      int64_t last = -1;
+      for (int c = 0; c < n_ball; c++) {
+        int64_t  best = INT64_MAX;
+        uint32_t bt   = 0;
+        for (int k = 0; k < 4; k++) {
+          for (uint32_t t = lo[k]; t < hi[k]; t++) {
+            const double4 r  = g.rec[t];
+            const int64_t gj = __double_as_longlong(r.w);
+            if (gj <= last || gj >= best || !in_ball(r, k)) continue;
             best = gj;
-            contribution(r, Pj, bx, by, bz);
+            bt   = t;
           }
         }
+        if (best == INT64_MAX) break;
+        process(g.rec[bt]);
+        last = best;
       }
-      if (best == INT64_MAX) break;
-      fx   = __dadd_rn(fx, bx);
-      fy   = __dadd_rn(fy, by);
-      fz   = __dadd_rn(fz, bz);
-      last = best;
     }
   }
 
@@ -305,15 +298,15 @@ int launch_collide(const DevState& s, const DevGrid& g, int crash_mode, double r
   const int      filter = s.n_global > s.n;
   int            own    = 0;
   cudaMemsetAsync(g.counters, 0, sizeof(unsigned long long), stream);
-  cudaMemsetAsync(g.count, 0, sizeof(uint32_t) * (size_t(g.n_buckets) + 1), stream);
+  cudaMemsetAsync(g.count, 0, sizeof(uint32_t) * (size_t(g.n_buckets) + 2), stream);
   if (filter) {
     box_reset_kernel<<<1, 32, 0, stream>>>(g.aabb);
     if (s.n > 0) box_kernel<<<unsigned(std::min<int64_t>((s.n + T - 1) / T, 296)), T, 0, stream>>>(s.gpos, s.shard_begin, s.n, g.aabb);
     own += 2;
   }
   count_kernel<<<nb, T, 0, stream>>>(s.gpos, n, s.shard_begin, s.n, filter, g.aabb, g.n_buckets - 1, g.count, g.bucket, g.rank);
-  cub::DeviceScan::ExclusiveSum(cub_tmp, cub_tmp_bytes, g.count, g.begin, int(g.n_buckets) + 1, stream);
-  scatter_kernel<<<nb, T, 0, stream>>>(s.gpos, n, g.bucket, g.rank, g.begin, g.rec);
+  cub::DeviceScan::ExclusiveSum(cub_tmp, cub_tmp_bytes, g.count, g.begin, int(g.n_buckets) + 2, stream);
+  scatter_kernel<<<nb, T, 0, stream>>>(s.gpos, n, g.bucket, g.rank, g.begin, g.n_buckets, g.rec);
   collide_kernel<<<unsigned((n + 127) / 128), 128, 0, stream>>>(s, g, crash_mode, rebounce);
   return own + 3;  // own kernels: [box_reset, box,] count, scatter, collide (CUB's scan kernels and the memsets are not counted)
 }

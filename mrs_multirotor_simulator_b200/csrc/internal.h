@@ -96,9 +96,9 @@ struct DevGrid {
   uint32_t  bits;
   uint32_t* bucket;     // [n_global] bucket of each UAV, 0xFFFFFFFF = not inserted (remote and outside this shard's box)
   uint32_t* rank;       // [n_global] arrival rank inside its bucket
-  uint32_t* count;      // [n_buckets+1] occupancy histogram (last entry stays 0)
-  uint32_t* begin;      // [n_buckets+1] exclusive scan of count; begin[n_buckets] = number of inserted UAVs
-  double4*  rec;        // [n_global] records {x,y,z, index bits} grouped by bucket
+  uint32_t* count;      // [n_buckets+2] occupancy histogram; [n_buckets] mirrors bucket 0, last entry stays 0
+  uint32_t* begin;      // [n_buckets+2] exclusive scan of count; begin[n_buckets] = number of inserted UAVs
+  double4*  rec;        // [2*n_global] records {x,y,z, index bits} grouped by bucket (+ the mirror copies of bucket 0)
   unsigned long long* aabb;  // [6] order-preserving encoding of min xyz / max xyz of this shard's positions
   int32_t*  pairs;      // [pair_cap][2]
   int64_t   pair_cap;

@@ -158,3 +158,40 @@ def test_c2_400_uav_scenario_with_rebounce():
             total_pairs += len(pg)
     assert_parity(orc, gpu, what="C2")
     assert total_pairs > 0
+
+
+def _row_hash(cy, cz):
+    """collide.cu row_hash (kept in step with the kernel; used only to aim a test at the table wrap)."""
+    m = 0xFFFFFFFF
+    h = ((cy & m) * 0x9E3779B1 & m) ^ (((cz & m) * 0x85EBCA77 + 0x165667B1) & m)
+    h ^= h >> 15
+    h = h * 0x2C1B3C6D & m
+    h ^= h >> 12
+    return h
+
+
+def test_stencil_row_across_the_end_of_the_bucket_table():
+    """Two x-adjacent cells whose buckets are B-1 and 0: found through the mirror bucket."""
+    n_buckets = 1024  # smallest table (n_global <= 512)
+    hits = []
+    for cy in range(-40, 40):
+        for cz in range(0, 4):
+            cx = (n_buckets - 1 - _row_hash(cy, cz)) % n_buckets  # bucket(cx) == B-1, bucket(cx+1) == 0
+            if cx < 200:
+                hits.append((cx, cy, cz))
+    assert len(hits) >= 4
+    xyz = []
+    for cx, cy, cz in hits[:8]:
+        xb = 4.0 * (cx + 1)  # boundary between cell cx and cx+1
+        y, z = 4.0 * cy + 2.0, 4.0 * cz + 2.0
+        xyz += [[xb - 0.2, y, z], [xb + 0.2, y, z], [xb + 0.45, y + 0.1, z]]
+    xyz = np.array(xyz)
+    n = len(xyz)
+    types = [af("x500")]
+    tou = np.zeros(n, dtype=np.int32)
+    arm, prop, mass = geometry(types, tou)
+    ref_pairs, ref_forces, _ = O.collide_snapshot(xyz, arm, prop, mass, False, 100.0, engine=ENGINE)
+    b, pairs, forces, _ = run_gpu_pass(types, tou, xyz, False, 100.0)
+    assert len(ref_pairs) >= 4 * len(hits[:8])
+    assert np.array_equal(sorted_pairs(ref_pairs), pairs)
+    assert np.array_equal(ref_forces, forces)
