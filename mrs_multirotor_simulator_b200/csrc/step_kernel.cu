@@ -827,9 +827,9 @@ __global__ void publish_positions_kernel(DevState s) {
   const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= s.n) return;
   double* gp = s.gpos + 3 * (s.shard_begin + i);
-  gp[0]      = s.st[0 * s.ld + i];
-  gp[1]      = s.st[1 * s.ld + i];
-  gp[2]      = s.st[2 * s.ld + i];
+  gp[0]      = s.st[tix(ST_ROWS, 0, i)];
+  gp[1]      = s.st[tix(ST_ROWS, 1, i)];
+  gp[2]      = s.st[tix(ST_ROWS, 2, i)];
 }
 
 // CTAs of the staged kernel that fit on the device (persistent grid), cached per instantiation
