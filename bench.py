@@ -191,6 +191,7 @@ def run_b200(args):
     import torch
 
     from mrs_multirotor_simulator_b200 import ACTUATOR_CMD, VELOCITY_HDG_RATE_CMD, UavBatch, _lib
+    from mrs_multirotor_simulator_b200.sharding import connect, shard_range
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -204,17 +205,12 @@ def run_b200(args):
         import torch.distributed as dist
 
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    n_local = N_UAVS // world
-    begin = rank * n_local
-    if rank == world - 1:
-        n_local = N_UAVS - begin
+    begin, n_local = shard_range(N_UAVS, world, rank)
 
     spawn, cmd = workload(begin, n_local)
     batch = UavBatch([x500_world()], spawn_xyz=spawn, n=n_local, device=local, n_global=N_UAVS, shard_begin=begin)
     if world > 1:
-        uid = [UavBatch.nccl_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        batch.comm_init_nccl(world, rank, uid[0])
+        connect(batch, dist)
     batch.set_input(ACTUATOR_CMD, np.zeros((n_local, 8)))
     batch.make_step(DT)
     batch.make_step(DT)

@@ -135,6 +135,9 @@ void mrsb_model_params_default(mrsb_model_params* out);
 void mrsb_model_params_finalize(mrsb_model_params* p);
 /* Header defaults of the five controller Params classes (same as config/controllers/ yaml). */
 void mrsb_controller_params_default(mrsb_controller_params* out);
+/* Mixer::calculateAllocation (CTL/mixer.hpp:72-101) for an airframe, no handle needed: normalised
+ * pseudo-inverse of the allocation matrix, row-major [n_motors][4] in out[MRSB_MAX_MOTORS*4]. */
+void mrsb_mixer_allocation_of(const mrsb_model_params* params, double* out);
 
 /* ---- lifetime: UavSystem(params, spawn_pos, spawn_heading) for every UAV (US:144-153) ----- */
 int mrsb_create(const mrsb_create_info* info, mrsb_handle* out);

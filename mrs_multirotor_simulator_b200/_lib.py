@@ -52,6 +52,7 @@ SIGNATURES = {
     "mrsb_model_params_default": (None, [C.POINTER(ModelParams)]),
     "mrsb_model_params_finalize": (None, [C.POINTER(ModelParams)]),
     "mrsb_controller_params_default": (None, [C.POINTER(ControllerParams)]),
+    "mrsb_mixer_allocation_of": (None, [C.POINTER(ModelParams), C.c_void_p]),
     "mrsb_create": (C.c_int, [C.POINTER(CreateInfo), C.POINTER(H)]),
     "mrsb_destroy": (C.c_int, [H]),
     "mrsb_sync": (C.c_int, [H]),

@@ -127,6 +127,12 @@ void mrsb_mixer_allocation(const mrsb_model_params& mp, double mix[MRSB_MAX_MOTO
   }
 }
 
+extern "C" void mrsb_mixer_allocation_of(const mrsb_model_params* params, double* out) {
+  double mix[MRSB_MAX_MOTORS][4];
+  mrsb_mixer_allocation(*params, mix);
+  std::memcpy(out, mix, sizeof(mix));
+}
+
 void mrsb_derive(const mrsb_model_params& mp, const mrsb_controller_params& cp, DevParams* d) {
   std::memset(d, 0, sizeof(*d));
   d->n_motors           = mp.n_motors;

@@ -69,6 +69,8 @@ def lib():
         L.orc_collide_port.restype = C.c_int64
         L.orc_collide_port.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_double, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_int64, C.c_int32]
+        L.orc_pid_update.restype = C.c_double
+        L.orc_pid_update.argtypes = [C.c_void_p] + [C.c_double] * 7
         L.orc_u01.restype = C.c_double
         L.orc_u01.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64]
         L.orc_model_params_default.argtypes = [C.c_void_p]
@@ -129,6 +131,11 @@ def params_from_dict(d):
         for m_ in range(n):
             p.allocation_matrix[r * MAX_MOTORS + m_] = float(A[r, m_]) * scale[r]
     return p
+
+
+def pid_update(state, kp, kd, ki, saturation, antiwindup, error, dt):
+    """PIDController::update on state = np.array([last_error, integral]) (modified in place)."""
+    return lib().orc_pid_update(_p(state), kp, kd, ki, saturation, antiwindup, error, dt)
 
 
 def u01(seed, stream, index):

@@ -62,6 +62,9 @@ void orc_handle_collisions(orc_swarm* s, int32_t enabled, int32_t crash, double 
 int64_t orc_collide_port(int64_t n, const double* xyz, const double* arm, const double* prop, const double* mass, int32_t crash_mode, double rebounce,
                          double* forces, uint8_t* crashed, int32_t* pairs, int64_t cap, int32_t n_threads);
 
+/* PIDController::update (CTL/pid.hpp:67-96) on caller-held state {last_error, integral}; returns the output */
+double orc_pid_update(double* state2, double kp, double kd, double ki, double saturation, double antiwindup, double error, double dt);
+
 /* counter-based RNG shared by tests and bench: splitmix64(seed + GOLDEN*(stream*2^32 + index)) -> [0,1) */
 double orc_u01(uint64_t seed, uint64_t stream, uint64_t index);
 

@@ -420,6 +420,17 @@ void orc_handle_collisions(orc_swarm* s, int32_t enabled, int32_t crash, double 
   }
 }
 
+double orc_pid_update(double* state2, double kp, double kd, double ki, double saturation, double antiwindup, double error, double dt) {
+  Pid p;
+  p.setParams(kp, kd, ki, saturation, antiwindup);
+  p.last_error    = state2[0];
+  p.integral      = state2[1];
+  const double u  = p.update(error, dt);
+  state2[0]       = p.last_error;
+  state2[1]       = p.integral;
+  return u;
+}
+
 double orc_u01(uint64_t seed, uint64_t stream, uint64_t index) {
   uint64_t z = seed + 0x9E3779B97F4A7C15ull * ((stream << 32) + index);
   z += 0x9E3779B97F4A7C15ull;

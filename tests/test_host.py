@@ -1,0 +1,95 @@
+"""CPU-only checks of the host-side logic of the product: parameter derivation, airframe data,
+YAML loader, sharding helpers, the command encoders of the UavSystem mirror."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from mrs_multirotor_simulator_b200 import AIRFRAMES, airframe, load_airframe_yaml, model_params
+from mrs_multirotor_simulator_b200 import _lib
+from mrs_multirotor_simulator_b200.sharding import gather_layout, shard_range
+from oracle import binding as O
+
+
+@pytest.mark.parametrize("name", sorted(AIRFRAMES))
+def test_param_derivation_matches_the_reference_formulas(name):
+    """J (uav_system_ros.cpp:664-671) and allocation scaling (:98-103): library == oracle, bit for bit."""
+    a = model_params(airframe(name))
+    b = O.params_from_dict(airframe(name))
+    assert list(a.J) == list(b.J)
+    assert list(a.allocation_matrix) == list(b.allocation_matrix)
+    for f in ("n_motors", "mass", "kf", "km", "prop_radius", "arm_length", "body_height", "motor_time_constant", "max_rpm", "min_rpm", "g"):
+        assert getattr(a, f) == getattr(b, f), f
+
+
+def test_default_model_params_are_the_x500_header_defaults():
+    p = _lib.ModelParams()
+    _lib.lib().mrsb_model_params_default(C.byref(p))
+    q = model_params(airframe("x500", takeoff_patch_enabled=True))
+    o = O.OrcModelParams()
+    O.lib().orc_model_params_default(C.byref(o))
+    assert bytes(p) == bytes(q) == bytes(o)  # multirotor_model.hpp:26-66
+    assert p.takeoff_patch_enabled == 1 and p.ground_enabled == 0
+
+
+@pytest.mark.parametrize("name", sorted(AIRFRAMES))
+def test_mixer_allocation_host_vs_oracle(name):
+    """Mixer::calculateAllocation (mixer.hpp:72-101): independent implementations agree to rounding."""
+    out = np.zeros((8, 4))
+    p = model_params(airframe(name))
+    _lib.lib().mrsb_mixer_allocation_of(C.byref(p), out.ctypes.data_as(C.c_void_p))
+    ref = O.OracleSwarm([airframe(name)], spawn_xyz=[[0, 0, 0]], n=1).get_mixer_allocation()
+    n = p.n_motors
+    assert np.max(np.abs(out - ref)) < 1e-12
+    assert np.allclose(np.linalg.norm(out[:n, :2], axis=1), 1.0) and set(np.unique(out[:n, 2])) <= {-1.0, 0.0, 1.0}
+    assert np.all(out[:n, 3] == 1.0) and not out[n:].any()
+
+
+def test_yaml_loader_reads_the_reference_schema(tmp_path):
+    y = tmp_path / "f550.yaml"
+    y.write_text("""
+f550:
+  n_motors: 6
+  mass: 2.3
+  arm_length: 0.27
+  body_height: 0.1
+  motor_time_constant: 0.03
+  air_resistance_coeff: 0.30
+  propulsion:
+    force_constant: 0.00000012216
+    moment_constant: 0.07
+    prop_radius: 0.11
+    allocation_matrix: [
+      1, -1, -0.5,  0.5,  0.5,   -0.5,
+      0, 0,  -0.87, 0.87, -0.87, 0.87,
+      1, -1, 1,     -1,   -1,    1,
+      1, 1,  1,     1,    1,     1
+    ]
+    rpm:
+      min: 1360
+      max: 9068
+""")
+    assert load_airframe_yaml(str(y)) == AIRFRAMES["f550"]
+
+
+def test_shard_ranges_tile_the_swarm():
+    for n, w in ((1 << 20, 8), (1000, 3), (7, 8), (5, 1)):
+        rs = [shard_range(n, w, r) for r in range(w)]
+        assert rs[0][0] == 0 and sum(c for _, c in rs) == n
+        assert all(rs[r][0] + rs[r][1] == rs[r + 1][0] for r in range(w - 1))
+        assert max(c for _, c in rs) - min(c for _, c in rs) <= 1
+    assert gather_layout(10, 2) == [(0, 15), (15, 15)]
+    with pytest.raises(ValueError):
+        shard_range(10, 2, 2)
+
+
+def test_command_encoders_follow_references_hpp():
+    from mrs_multirotor_simulator_b200 import uav_system as U
+
+    assert U._encode(U.Position(position=np.array([1.0, 2, 3]), heading=0.5)) == (10, [1.0, 2.0, 3.0, 0.5])
+    assert U._encode(U.VelocityHdgRate(velocity=np.array([1.0, 2, 3]), heading_rate=0.5)) == (8, [1.0, 2.0, 3.0, 0.5])
+    mode, pl = U._encode(U.Attitude(orientation=np.arange(9.0).reshape(3, 3), throttle=0.4))
+    assert mode == 4 and pl == [0.0, 3.0, 6.0, 1.0, 4.0, 7.0, 2.0, 5.0, 8.0, 0.4]  # column-major
+    assert U._encode(U.TiltHdgRate())[1] == [1.0, 0.0, 0.0, 0.0, 0.0]  # Vector3d::Identity() default (references.hpp:123)
+    with pytest.raises(TypeError):
+        U._encode(object())
