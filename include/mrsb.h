@@ -177,6 +177,20 @@ int mrsb_set_input(mrsb_handle h, int32_t mode, int64_t n, const int32_t* idx, c
 /* Same, but idx/payload are DEVICE pointers valid on the handle's device; no host round trip. */
 int mrsb_set_input_device(mrsb_handle h, int32_t mode, int64_t n, const int32_t* idx_dev, const double* payload_dev, int32_t stride);
 
+/* Pipelined variants for host loops that feed commands and read poses EVERY tick (the reference
+ * node does both: ROS command callbacks in, publishPoses out, SIM:215).  Both return at once:
+ *  - mrsb_set_input_async: whole-batch setInput; the host rows (pinned memory recommended) are
+ *    copied on a dedicated upload stream into one of two staging buffers while earlier ticks are
+ *    still computing; the handle's stream waits for the copy before applying the command.  The
+ *    caller must leave `payload` untouched until a later mrsb_sync / mrsb_wait_uploads.
+ *  - mrsb_get_positions_async: snapshots the positions as of the work enqueued so far and copies
+ *    them ([n_local][3] doubles) to `out_xyz` on a dedicated download stream while later ticks
+ *    compute; `out_xyz` is valid after mrsb_sync (or mrsb_wait_downloads). */
+int mrsb_set_input_async(mrsb_handle h, int32_t mode, const double* payload, int32_t stride);
+int mrsb_get_positions_async(mrsb_handle h, double* out_xyz);
+int mrsb_wait_uploads(mrsb_handle h);
+int mrsb_wait_downloads(mrsb_handle h);
+
 /* ---- feed-forwards: UavSystem::setFeedforward overloads (US:254-272); sticky, never cleared
  * by the reference (US:112-115).  Row layout [4]: xyz + heading or heading_rate.  mrsb_clear_
  * feedforward is an extension (the reference offers no way to unset the std::optional). */

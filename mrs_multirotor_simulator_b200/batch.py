@@ -117,6 +117,14 @@ class UavBatch:
         """payload_ptr / idx_ptr: raw device addresses (e.g. torch tensor .data_ptr())."""
         check(self._L.mrsb_set_input_device(self.h, mode, self.n if n is None else n, idx_ptr, payload_ptr, stride))
 
+    def set_input_async(self, mode, payload_ptr, stride):
+        """Whole-batch setInput from host rows at address `payload_ptr` (pinned), uploaded on its own stream."""
+        check(self._L.mrsb_set_input_async(self.h, mode, payload_ptr, stride))
+
+    def get_positions_async(self, out_ptr):
+        """Positions [n][3] -> host address `out_ptr` (pinned), downloaded on its own stream; valid after sync()."""
+        check(self._L.mrsb_get_positions_async(self.h, out_ptr))
+
     def set_feedforward(self, kind, payload, idx=None):
         """kind: 'acceleration_hdg_rate' | 'acceleration_hdg' | 'velocity_hdg' | 'velocity_hdg_rate' (uav_system.hpp:254-272)."""
         idx = _idx(idx)

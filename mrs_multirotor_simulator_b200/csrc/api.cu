@@ -122,6 +122,14 @@ struct mrsb_sim {
   std::vector<int64_t> shard_begin_of, shard_count_of;
   bool                 equal_shards = true;
 
+  // pipelined host I/O (mrsb_set_input_async / mrsb_get_positions_async)
+  cudaStream_t up_stream = nullptr, down_stream = nullptr;
+  double*      d_up[2]   = {nullptr, nullptr};  // staged command rows
+  size_t       d_up_bytes = 0;
+  double*      d_snap[2] = {nullptr, nullptr};  // position snapshots [n_local][3]
+  cudaEvent_t  ev_up[2] = {nullptr, nullptr}, ev_applied[2] = {nullptr, nullptr}, ev_snap[2] = {nullptr, nullptr}, ev_down[2] = {nullptr, nullptr};
+  uint64_t     n_up = 0, n_down = 0;
+
   int64_t n_steps = 0, n_passes = 0, n_launches = 0;
 };
 
@@ -237,6 +245,14 @@ static int dalloc(T** p, size_t count) {
   return MRSB_OK;
 }
 
+static void note_mode(mrsb_sim* h, int mode, int64_t n, bool all) {
+  if (all && n == h->ds.n) {
+    h->uniform_mode = mode;
+  } else if (n > 0 && h->uniform_mode != mode) {
+    h->uniform_mode = -1;
+  }
+}
+
 static int stride_of(int mode) {
   switch (mode) {
     case MRSB_ACTUATOR_CMD:
@@ -300,6 +316,16 @@ int mrsb_destroy(mrsb_handle h) {
   if (!h) return MRSB_OK;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->up_stream) cudaStreamSynchronize(h->up_stream);
+  if (h->down_stream) cudaStreamSynchronize(h->down_stream);
+  for (int k = 0; k < 2; k++) {
+    if (h->d_up[k]) cudaFree(h->d_up[k]);
+    if (h->d_snap[k]) cudaFree(h->d_snap[k]);
+    for (cudaEvent_t e : {h->ev_up[k], h->ev_applied[k], h->ev_snap[k], h->ev_down[k]})
+      if (e) cudaEventDestroy(e);
+  }
+  if (h->up_stream) cudaStreamDestroy(h->up_stream);
+  if (h->down_stream) cudaStreamDestroy(h->down_stream);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   void* ptrs[] = {h->ds.st,     h->ds.vprev,  h->ds.rpm,      h->ds.pid,      h->ds.fext,         h->ds.mext,       h->ds.imu,    h->ds.initz,
                   h->ds.cmd,    h->ds.ff,     h->ds.flags,    h->ds.mode,     h->ds.gpos,         h->d_params,      h->d_pset,    h->d_stage,
@@ -444,6 +470,82 @@ int mrsb_create(const mrsb_create_info* info, mrsb_handle* out) {
 int mrsb_sync(mrsb_handle h) {
   GUARD(h);
   CU(cudaStreamSynchronize(h->stream));
+  if (h->up_stream) CU(cudaStreamSynchronize(h->up_stream));
+  if (h->down_stream) CU(cudaStreamSynchronize(h->down_stream));
+  return MRSB_OK;
+}
+
+static int ensure_pipeline(mrsb_sim* h) {
+  if (h->up_stream) return MRSB_OK;
+  CU(cudaStreamCreateWithFlags(&h->up_stream, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&h->down_stream, cudaStreamNonBlocking));
+  for (int k = 0; k < 2; k++) {
+    CU(cudaEventCreateWithFlags(&h->ev_up[k], cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&h->ev_applied[k], cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&h->ev_snap[k], cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&h->ev_down[k], cudaEventDisableTiming));
+    CU(cudaMalloc(&h->d_snap[k], sizeof(double) * 3 * size_t(std::max<int64_t>(h->ds.n, 1))));
+  }
+  return MRSB_OK;
+}
+
+int mrsb_set_input_async(mrsb_handle h, int32_t mode, const double* payload, int32_t stride) {
+  GUARD(h);
+  if (mode <= MRSB_INPUT_UNKNOWN || mode > MRSB_POSITION_CMD) return fail(MRSB_ERR_INVALID, "mode %d carries no payload", mode);
+  if (!payload) return fail(MRSB_ERR_INVALID, "null payload");
+  if (stride < (mode == MRSB_ACTUATOR_CMD ? 1 : stride_of(mode))) return fail(MRSB_ERR_INVALID, "stride %d too small for mode %d", stride, mode);
+  int rc = ensure_pipeline(h);
+  if (rc) return rc;
+  const int64_t n     = h->ds.n;
+  const size_t  bytes = sizeof(double) * size_t(n) * size_t(stride);
+  if (bytes > h->d_up_bytes) {
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaStreamSynchronize(h->up_stream));
+    for (int k = 0; k < 2; k++) {
+      if (h->d_up[k]) CU(cudaFree(h->d_up[k]));
+      CU(cudaMalloc(&h->d_up[k], std::max<size_t>(bytes, 256)));
+    }
+    h->d_up_bytes = bytes;
+    h->n_up       = 0;
+  }
+  const int k = int(h->n_up & 1);
+  if (h->n_up >= 2) CU(cudaStreamWaitEvent(h->up_stream, h->ev_applied[k], 0));  // the staging buffer was consumed two uploads ago
+  CU(cudaMemcpyAsync(h->d_up[k], payload, bytes, cudaMemcpyHostToDevice, h->up_stream));
+  CU(cudaEventRecord(h->ev_up[k], h->up_stream));
+  CU(cudaStreamWaitEvent(h->stream, h->ev_up[k], 0));
+  h->n_launches += launch_scatter_input(h->ds, mode, n, nullptr, h->d_up[k], stride, h->stream);
+  CU(cudaEventRecord(h->ev_applied[k], h->stream));
+  h->n_up++;
+  note_mode(h, mode, n, true);
+  CU(cudaGetLastError());
+  return MRSB_OK;
+}
+
+int mrsb_get_positions_async(mrsb_handle h, double* out_xyz) {
+  GUARD(h);
+  if (!out_xyz) return fail(MRSB_ERR_INVALID, "null output");
+  int rc = ensure_pipeline(h);
+  if (rc) return rc;
+  const int    k     = int(h->n_down & 1);
+  const size_t bytes = sizeof(double) * 3 * size_t(h->ds.n);
+  if (h->n_down >= 2) CU(cudaStreamWaitEvent(h->stream, h->ev_down[k], 0));  // the snapshot buffer was downloaded two reads ago
+  CU(cudaMemcpyAsync(h->d_snap[k], h->ds.gpos + 3 * h->ds.shard_begin, bytes, cudaMemcpyDeviceToDevice, h->stream));
+  CU(cudaEventRecord(h->ev_snap[k], h->stream));
+  CU(cudaStreamWaitEvent(h->down_stream, h->ev_snap[k], 0));
+  CU(cudaMemcpyAsync(out_xyz, h->d_snap[k], bytes, cudaMemcpyDeviceToHost, h->down_stream));
+  CU(cudaEventRecord(h->ev_down[k], h->down_stream));
+  h->n_down++;
+  return MRSB_OK;
+}
+
+int mrsb_wait_uploads(mrsb_handle h) {
+  GUARD(h);
+  if (h->up_stream) CU(cudaStreamSynchronize(h->up_stream));
+  return MRSB_OK;
+}
+int mrsb_wait_downloads(mrsb_handle h) {
+  GUARD(h);
+  if (h->down_stream) CU(cudaStreamSynchronize(h->down_stream));
   return MRSB_OK;
 }
 int64_t mrsb_n_local(mrsb_handle h) {
@@ -459,14 +561,6 @@ void* mrsb_get_stream(mrsb_handle h) {
 // ------------------------------------------------------------------------------------------
 // commands
 // ------------------------------------------------------------------------------------------
-static void note_mode(mrsb_sim* h, int mode, int64_t n, bool all) {
-  if (all && n == h->ds.n) {
-    h->uniform_mode = mode;
-  } else if (n > 0 && h->uniform_mode != mode) {
-    h->uniform_mode = -1;
-  }
-}
-
 int mrsb_set_input_device(mrsb_handle h, int32_t mode, int64_t n, const int32_t* idx_dev, const double* payload_dev, int32_t stride) {
   GUARD(h);
   if (mode < MRSB_INPUT_UNKNOWN || mode > MRSB_POSITION_CMD) return fail(MRSB_ERR_INVALID, "mode %d is not an INPUT_MODE", mode);

@@ -300,3 +300,34 @@ def test_uav_system_facade_single():
     assert np.allclose(st.x, [4.99966878, -2.99316222, 3.99492282], atol=2e-8)
     assert abs(np.arctan2(st.R[1, 0], st.R[0, 0]) - 0.99999634) < 1e-7
     assert st.motor_rpm.shape == (4,) and not u.hasCrashed()
+
+
+def test_pipelined_host_io_equals_blocking_io():
+    """mrsb_set_input_async / mrsb_get_positions_async (upload and download on their own streams,
+    double-buffered) deliver exactly what the blocking setInput / getState pair does."""
+    import torch
+
+    from mrs_multirotor_simulator_b200 import UavBatch
+
+    n, ticks = 5000, 40
+    spawn = grid_spawn(n, z=10.0)
+    a = UavBatch([af("x500")], spawn_xyz=spawn, n=n)
+    b = UavBatch([af("x500")], spawn_xyz=spawn, n=n)
+    cmds = [torch.from_numpy(np.stack([rand(t, 1, n, -2, 2), rand(t, 2, n, -2, 2), rand(t, 3, n, -1, 1), rand(t, 4, n, -1, 1)], axis=1)).pin_memory()
+            for t in range(ticks)]
+    outs = [torch.zeros((n, 3), dtype=torch.float64).pin_memory() for _ in range(ticks)]
+    ref = []
+    for t in range(ticks):
+        a.set_input(O.VELOCITY_HDG_RATE_CMD, cmds[t].numpy())
+        a.make_step(0.01)
+        ref.append(a.get_state(fields=("x",))["x"].copy())
+    for t in range(ticks):  # nothing blocks here: all ticks are enqueued back to back
+        b.set_input_async(O.VELOCITY_HDG_RATE_CMD, cmds[t].data_ptr(), 4)
+        b.make_step(0.01)
+        b.get_positions_async(outs[t].data_ptr())
+    b.sync()
+    for t in range(ticks):
+        assert np.array_equal(outs[t].numpy(), ref[t]), t
+    fa, fb = a.get_full_state(), b.get_full_state()
+    for k in fa:
+        assert np.array_equal(fa[k], fb[k]), k
