@@ -175,6 +175,9 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+EXCHANGE = {0: "none (single shard)", 1: "NCCL all-gather of packed xyz per tick", 2: "fused: stepping kernel stores positions into all peers over NVLink (CUDA IPC), flag hand-shake per tick"}
+
+
 def workload_config(n_gpus, l2_note):
     cfg = {"workload": "C4: 1,048,576 x500 UAVs, 1024x1024 grid 4 m pitch, VelocityHdgRate commands, dt=0.01, K=1, ground plane + mutual collisions "
                        "(rebounce 100) every tick", "n_uavs": N_UAVS, "dt": DT, "k_substeps": 1, "collisions": "enabled, crash=false, rebounce=100",
@@ -355,7 +358,7 @@ def run_b200(args):
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": workload_config(world, l2_note), "clocks": clocks,
+            "data": "synthetic", "config": dict(workload_config(world, l2_note), exchange=EXCHANGE[batch.exchange_mode()]), "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(cmd_host.numel() * 8), "d2h_bytes_per_step": int(pos_host[0].numel() * 8),
                     "steps": n_e2e, "blocking_api_value": N_UAVS * n_e2e / e2e_blocking_s,
                     "note": "per rank, every tick, via the C ABI: VelocityHdgRate rows H2D from pinned memory (mrsb_set_input_async), makeStep, "

@@ -278,6 +278,12 @@ int mrsb_get_counters(mrsb_handle h, int64_t* out5);
  *      (this shard's slice, filled by mrsb_publish_positions, starts at shard_begin*3).        */
 int mrsb_nccl_unique_id(void* out128);
 int mrsb_comm_init_nccl(mrsb_handle h, int32_t n_ranks, int32_t rank, const void* unique_id128);
+/* How mrsb_handle_collisions exchanges positions: 0 = single shard, 1 = NCCL all-gather,
+ * 2 = fused: peers mapped over CUDA IPC at mrsb_comm_init_nccl, the stepping kernel stores every
+ * position into all peers' buffers over NVLink and the collision pass only hand-shakes
+ * (set MRSB_NO_P2P=1 to force mode 1).  In sharded runs every rank must issue the same sequence
+ * of mrsb_make_step / position-writing calls, as with any collective. */
+int mrsb_exchange_mode(mrsb_handle h);
 int mrsb_gather_buffer(mrsb_handle h, void** device_ptr, size_t* bytes);
 int mrsb_publish_positions(mrsb_handle h);
 int mrsb_handle_collisions_gathered(mrsb_handle h);

@@ -110,6 +110,7 @@ SIGNATURES = {
     "mrsb_get_counters": (C.c_int, [H, C.c_void_p]),
     "mrsb_nccl_unique_id": (C.c_int, [C.c_void_p]),
     "mrsb_comm_init_nccl": (C.c_int, [H, C.c_int32, C.c_int32, C.c_void_p]),
+    "mrsb_exchange_mode": (C.c_int, [H]),
     "mrsb_gather_buffer": (C.c_int, [H, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
     "mrsb_publish_positions": (C.c_int, [H]),
     "mrsb_handle_collisions_gathered": (C.c_int, [H]),

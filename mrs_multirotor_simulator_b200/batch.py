@@ -290,6 +290,10 @@ class UavBatch:
         buf = (C.c_char * 128).from_buffer_copy(unique_id)
         check(self._L.mrsb_comm_init_nccl(self.h, n_ranks, rank, buf))
 
+    def exchange_mode(self):
+        """0 single shard, 1 NCCL all-gather per tick, 2 fused peer stores from the stepping kernel."""
+        return int(self._L.mrsb_exchange_mode(self.h))
+
     def gather_buffer(self):
         p = C.c_void_p()
         nbytes = C.c_size_t()

@@ -122,6 +122,18 @@ struct mrsb_sim {
   std::vector<int64_t> shard_begin_of, shard_count_of;
   bool                 equal_shards = true;
 
+  // fused position exchange over peer memory (set up by mrsb_comm_init_nccl when every peer is reachable)
+  bool                 p2p       = false;
+  double*              gbuf[2]   = {nullptr, nullptr};  // double-buffered gather buffer (parity flips every step)
+  int                  parity    = 0;
+  bool                 pushed    = false;  // the current buffer was last written by a pushing step kernel
+  unsigned long long   epoch     = 0;
+  double**             d_peers[2] = {nullptr, nullptr};  // device arrays [n_ranks] of the peers' gbuf[parity]
+  unsigned long long*  d_flags   = nullptr;              // [n_ranks] written by the peers
+  unsigned long long** d_peer_flags = nullptr;           // device array [n_ranks] of the peers' d_flags
+  std::vector<void*>   ipc_opened;
+  int*                 h_status  = nullptr;              // pinned, mapped: set by the wait kernel on time-out
+
   // pipelined host I/O (mrsb_set_input_async / mrsb_get_positions_async)
   cudaStream_t up_stream = nullptr, down_stream = nullptr;
   double*      d_up[2]   = {nullptr, nullptr};  // staged command rows
@@ -300,6 +312,72 @@ static int repoint(mrsb_sim* h, int64_t n, const int32_t* idx, Edit edit) {
   return MRSB_OK;
 }
 
+// Fused exchange set-up: a second gather buffer, this rank's flag slots, and IPC mappings of every
+// peer's two buffers and flags (handles travel through one NCCL all-gather of raw bytes).
+static int setup_p2p(mrsb_sim* h) {
+  const int    G     = h->n_ranks;
+  const size_t bytes = sizeof(double) * 3 * size_t(h->ds.n_global);
+  h->gbuf[0]         = h->ds.gpos;
+  CU(cudaMalloc(&h->gbuf[1], std::max<size_t>(bytes, 16)));
+  CU(cudaMemcpy(h->gbuf[1], h->gbuf[0], bytes, cudaMemcpyDeviceToDevice));
+  CU(cudaMalloc(&h->d_flags, sizeof(unsigned long long) * G));
+  CU(cudaMemset(h->d_flags, 0, sizeof(unsigned long long) * G));
+  CU(cudaHostAlloc(&h->h_status, sizeof(int), cudaHostAllocMapped));
+  *h->h_status = 0;
+  struct Handles {
+    cudaIpcMemHandle_t buf[2], flags;
+  };
+  Handles mine;
+  CU(cudaIpcGetMemHandle(&mine.buf[0], h->gbuf[0]));
+  CU(cudaIpcGetMemHandle(&mine.buf[1], h->gbuf[1]));
+  CU(cudaIpcGetMemHandle(&mine.flags, h->d_flags));
+  Handles* d_all = nullptr;
+  CU(cudaMalloc(&d_all, sizeof(Handles) * G));
+  CU(cudaMemcpyAsync(d_all + h->rank, &mine, sizeof(Handles), cudaMemcpyHostToDevice, h->stream));
+  NC(g_nccl.AllGather(d_all + h->rank, d_all, sizeof(Handles), ncclChar, h->comm, h->stream));
+  std::vector<Handles> all;
+  all.resize(static_cast<size_t>(G));
+  CU(cudaMemcpyAsync(all.data(), d_all, sizeof(Handles) * G, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  CU(cudaFree(d_all));
+  std::vector<double*>             peers0(static_cast<size_t>(G), nullptr), peers1(static_cast<size_t>(G), nullptr);
+  std::vector<unsigned long long*> pflags(static_cast<size_t>(G), nullptr);
+  for (int r = 0; r < G; r++) {
+    if (r == h->rank) {
+      peers0[size_t(r)] = h->gbuf[0];
+      peers1[size_t(r)] = h->gbuf[1];
+      pflags[size_t(r)] = h->d_flags;
+      continue;
+    }
+    void* p = nullptr;
+    CU(cudaIpcOpenMemHandle(&p, all[size_t(r)].buf[0], cudaIpcMemLazyEnablePeerAccess));
+    h->ipc_opened.push_back(p);
+    peers0[size_t(r)] = static_cast<double*>(p);
+    CU(cudaIpcOpenMemHandle(&p, all[size_t(r)].buf[1], cudaIpcMemLazyEnablePeerAccess));
+    h->ipc_opened.push_back(p);
+    peers1[size_t(r)] = static_cast<double*>(p);
+    CU(cudaIpcOpenMemHandle(&p, all[size_t(r)].flags, cudaIpcMemLazyEnablePeerAccess));
+    h->ipc_opened.push_back(p);
+    pflags[size_t(r)] = static_cast<unsigned long long*>(p);
+  }
+  CU(cudaMalloc(&h->d_peers[0], sizeof(double*) * G));
+  CU(cudaMalloc(&h->d_peers[1], sizeof(double*) * G));
+  CU(cudaMalloc(&h->d_peer_flags, sizeof(unsigned long long*) * G));
+  CU(cudaMemcpy(h->d_peers[0], peers0.data(), sizeof(double*) * G, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(h->d_peers[1], peers1.data(), sizeof(double*) * G, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(h->d_peer_flags, pflags.data(), sizeof(unsigned long long*) * G, cudaMemcpyHostToDevice));
+  // everybody must have opened everybody's memory before the first push: one more (tiny) collective
+  unsigned long long* d_tmp = nullptr;
+  CU(cudaMalloc(&d_tmp, sizeof(unsigned long long) * G));
+  NC(g_nccl.AllGather(d_tmp + h->rank, d_tmp, sizeof(unsigned long long), ncclChar, h->comm, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  CU(cudaFree(d_tmp));
+  h->parity   = 0;
+  h->ds.peers = nullptr;  // set per step
+  h->p2p      = true;
+  return MRSB_OK;
+}
+
 extern "C" {
 
 const char* mrsb_last_error(void) {
@@ -326,6 +404,12 @@ int mrsb_destroy(mrsb_handle h) {
   }
   if (h->up_stream) cudaStreamDestroy(h->up_stream);
   if (h->down_stream) cudaStreamDestroy(h->down_stream);
+  for (void* p : h->ipc_opened) cudaIpcCloseMemHandle(p);
+  if (h->gbuf[1] && h->gbuf[1] != h->ds.gpos) cudaFree(h->gbuf[1]);
+  if (h->gbuf[0] && h->gbuf[0] != h->ds.gpos) cudaFree(h->gbuf[0]);
+  for (void* p : {(void*)h->d_peers[0], (void*)h->d_peers[1], (void*)h->d_flags, (void*)h->d_peer_flags})
+    if (p) cudaFree(p);
+  if (h->h_status) cudaFreeHost(h->h_status);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   void* ptrs[] = {h->ds.st,     h->ds.vprev,  h->ds.rpm,      h->ds.pid,      h->ds.fext,         h->ds.mext,       h->ds.imu,    h->ds.initz,
                   h->ds.cmd,    h->ds.ff,     h->ds.flags,    h->ds.mode,     h->ds.gpos,         h->d_params,      h->d_pset,    h->d_stage,
@@ -684,6 +768,13 @@ int mrsb_clear_feedforward(mrsb_handle h, int64_t n, const int32_t* idx) {
 static int exchange_positions(mrsb_sim* h) {
   if (h->n_ranks <= 1) return MRSB_OK;
   if (!h->comm) return fail(MRSB_ERR_STATE, "sharded handle (n_global > n_local) without a communicator: call mrsb_comm_init_nccl, or use mrsb_gather_buffer + mrsb_handle_collisions_gathered");
+  if (h->p2p && h->pushed) {
+    // the step kernel already stored this shard's positions into every peer's buffer: only the
+    // hand-shake "my epoch has landed" / "everybody's has" is left
+    h->n_launches += launch_p2p_signal(h->d_peer_flags, h->n_ranks, h->rank, h->epoch, h->stream);
+    h->n_launches += launch_p2p_wait(h->d_flags, h->n_ranks, h->rank, h->epoch, h->h_status, h->stream);
+    return MRSB_OK;
+  }
   double* buf = h->ds.gpos;
   if (h->equal_shards) {
     NC(g_nccl.AllGather(buf + 3 * h->ds.shard_begin, buf, size_t(3 * h->ds.n), ncclDouble, h->comm, h->stream));
@@ -710,6 +801,14 @@ int mrsb_make_step(mrsb_handle h, double dt, int32_t k_substeps) {
   if (k_substeps < 1) return fail(MRSB_ERR_INVALID, "k_substeps must be >= 1");
   int rc = flush_params(h);
   if (rc) return rc;
+  if (h->p2p) {
+    if (*h->h_status) return fail(MRSB_ERR_STATE, "peer position exchange timed out (a rank stopped stepping)");
+    h->parity ^= 1;
+    h->ds.gpos  = h->gbuf[h->parity];
+    h->ds.peers = h->d_peers[h->parity];
+    h->epoch++;
+    h->pushed = true;
+  }
   h->n_launches += launch_step(h->ds, dt, k_substeps, h->uniform_mode, h->uniform_nm, h->any_moment, h->stream);
   h->n_steps += k_substeps;
   CU(cudaGetLastError());
@@ -796,7 +895,10 @@ int mrsb_set_state(mrsb_handle h, int64_t n, const int32_t* idx, const double* x
   if (R && !rc) rc = put_rows(h, h->ds.st, ST_ROWS, 6, 9, n, idx, R, 9, 0);
   if (omega && !rc) rc = put_rows(h, h->ds.st, ST_ROWS, 15, 3, n, idx, omega, 3, 0);
   if (motor_rpm && !rc) rc = put_rows(h, h->ds.rpm, MRSB_NM, 0, MRSB_NM, n, idx, motor_rpm, MRSB_NM, 0);
-  if (x && !rc) h->n_launches += launch_publish_positions(h->ds, h->stream);
+  if (x && !rc) {
+    h->n_launches += launch_publish_positions(h->ds, h->stream);
+    h->pushed = false;
+  }
   return rc;
 }
 
@@ -814,6 +916,7 @@ int mrsb_set_state_pos(mrsb_handle h, int64_t n, const int32_t* idx, const doubl
   CU(cudaMemcpyAsync(d_xyz, xyz, sizeof(double) * 3 * size_t(n), cudaMemcpyHostToDevice, h->stream));
   CU(cudaMemcpyAsync(d_hdg, heading, sizeof(double) * size_t(n), cudaMemcpyHostToDevice, h->stream));
   h->n_launches += launch_set_state_pos(h->ds, n, d_idx, d_xyz, d_hdg, h->stream);
+  h->pushed = false;
   CU(cudaGetLastError());
   return MRSB_OK;
 }
@@ -1089,7 +1192,21 @@ int mrsb_comm_init_nccl(mrsb_handle h, int32_t n_ranks, int32_t rank, const void
     if (tab[2 * size_t(r) + 1] != h->ds.n || tab[2 * size_t(r)] != int64_t(r) * h->ds.n) h->equal_shards = false;
   }
   if (covered != h->ds.n_global) return fail(MRSB_ERR_INVALID, "shards cover %lld UAVs, n_global is %lld", (long long)covered, (long long)h->ds.n_global);
+  h->ds.n_ranks = n_ranks;
+  h->ds.rank    = rank;
+  if (n_ranks > 1 && n_ranks <= 32 && !getenv("MRSB_NO_P2P")) {
+    if (setup_p2p(h) != MRSB_OK) {  // no peer access (or IPC refused): the NCCL all-gather stays
+      cudaGetLastError();
+      h->p2p      = false;
+      h->ds.peers = nullptr;
+    }
+  }
   return MRSB_OK;
+}
+
+int mrsb_exchange_mode(mrsb_handle h) {
+  if (!h) return -1;
+  return h->n_ranks <= 1 ? 0 : (h->p2p ? 2 : 1);
 }
 
 int mrsb_gather_buffer(mrsb_handle h, void** device_ptr, size_t* bytes) {
@@ -1101,6 +1218,7 @@ int mrsb_gather_buffer(mrsb_handle h, void** device_ptr, size_t* bytes) {
 
 int mrsb_publish_positions(mrsb_handle h) {
   GUARD(h);
+  h->pushed = false;
   h->n_launches += launch_publish_positions(h->ds, h->stream);
   CU(cudaGetLastError());
   return MRSB_OK;

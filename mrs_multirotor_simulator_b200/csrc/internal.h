@@ -88,6 +88,10 @@ struct DevState {
   double*  gpos;  // [n_global][3] packed positions: this shard's slice is written by the step kernel
   int64_t  shard_begin;
   int64_t  n_global;
+  // fused position exchange (sharded runs with peer access): the step kernel also stores its positions
+  // into every peer's gather buffer over NVLink.  peers[r] = rank r's buffer (same parity as gpos).
+  double* const* peers;  // device array [n_ranks], nullptr = exchange by NCCL all-gather instead
+  int32_t  n_ranks, rank;
 };
 
 // collision pass workspace
@@ -110,6 +114,9 @@ int launch_step(const DevState& s, double dt, int k_substeps, int uniform_mode, 
 int launch_collide(const DevState& s, const DevGrid& g, int crash_mode, double rebounce, void* cub_tmp, size_t cub_tmp_bytes, cudaStream_t stream);
 size_t collide_tmp_bytes(int64_t n_global);
 int launch_publish_positions(const DevState& s, cudaStream_t stream);
+// cross-GPU hand-shake of the fused exchange: tell every peer "my positions of `epoch` have landed", wait for theirs
+int launch_p2p_signal(unsigned long long* const* peer_flags, int n_ranks, int rank, unsigned long long epoch, cudaStream_t stream);
+int launch_p2p_wait(const unsigned long long* flags, int n_ranks, int rank, unsigned long long epoch, int* status, cudaStream_t stream);
 
 int launch_scatter_input(const DevState& s, int mode, int64_t n, const int32_t* idx_dev, const double* payload_dev, int stride, cudaStream_t stream);
 // payload[k][0..rows) <-> rows [row0, row0+rows) of a tiled array with `rows_total` components

@@ -733,10 +733,21 @@ DEV void step_uav(const DevState& s, const TileIn& in, const int64_t tile, const
   if (valid) {
     if (new_flags != flags0) s.flags[i] = new_flags;
     // packed position for the collision pass / the cross-shard all-gather
-    double* gp = s.gpos + 3 * (s.shard_begin + i);
-    gp[0]      = x.x;
-    gp[1]      = x.y;
-    gp[2]      = x.z;
+    const int64_t go = 3 * (s.shard_begin + i);
+    double*       gp = s.gpos + go;
+    gp[0]            = x.x;
+    gp[1]            = x.y;
+    gp[2]            = x.z;
+    if (s.peers) {
+      // fused all-gather: the same 24 bytes go straight into every peer's buffer (posted NVLink stores)
+      for (int r = 0; r < s.n_ranks; r++) {
+        if (r == s.rank) continue;
+        double* pp = s.peers[r] + go;
+        pp[0]      = x.x;
+        pp[1]      = x.y;
+        pp[2]      = x.z;
+      }
+    }
   }
 #undef LD
 #undef ST
@@ -916,6 +927,42 @@ int launch_step(const DevState& s, double dt, int k_substeps, int uniform_mode, 
       launch_nm<0>(s, dt, k_substeps, uniform_mode, any_moment, stream);
       break;
   }
+  return 1;
+}
+
+namespace {
+__global__ void p2p_signal_kernel(unsigned long long* const* peer_flags, int n_ranks, int rank, unsigned long long epoch) {
+  __threadfence_system();
+  const int r = threadIdx.x;
+  if (r < n_ranks && r != rank) *reinterpret_cast<volatile unsigned long long*>(peer_flags[r] + rank) = epoch;
+}
+// one lane per peer spins (bounded) on this rank's own flag slots, which the peers write over NVLink
+__global__ void p2p_wait_kernel(const unsigned long long* flags, int n_ranks, int rank, unsigned long long epoch, int* status, long long budget) {
+  const int r = threadIdx.x;
+  if (r < n_ranks && r != rank) {
+    const long long t0 = clock64();
+    while (*reinterpret_cast<const volatile unsigned long long*>(flags + r) < epoch) {
+      if (clock64() - t0 > budget) {  // a peer is gone; report instead of hanging the GPU
+        *status = 1;
+        break;
+      }
+      __nanosleep(64);
+    }
+  }
+}
+}  // namespace
+
+int launch_p2p_signal(unsigned long long* const* peer_flags, int n_ranks, int rank, unsigned long long epoch, cudaStream_t stream) {
+  p2p_signal_kernel<<<1, 32, 0, stream>>>(peer_flags, n_ranks, rank, epoch);
+  return 1;
+}
+int launch_p2p_wait(const unsigned long long* flags, int n_ranks, int rank, unsigned long long epoch, int* status, cudaStream_t stream) {
+  static long long budget = 0;
+  if (!budget) {
+    const char* e = getenv("MRSB_P2P_TIMEOUT_MS");
+    budget        = (e ? atoll(e) : 3000LL) * 2000000LL;  // ~2 GHz SM clock
+  }
+  p2p_wait_kernel<<<1, 32, 0, stream>>>(flags, n_ranks, rank, epoch, status, budget);
   return 1;
 }
 
