@@ -528,8 +528,12 @@ int mrsb_create(const mrsb_create_info* info, mrsb_handle* out) {
   {
     DevGrid&     g  = h->grid;
     const size_t ng = size_t(std::max<int64_t>(s.n_global, 1));
-    uint32_t     bits = 10;
-    while ((size_t(1) << bits) < 2 * ng && bits < 30) bits++;
+    // >= 2 buckets per inserted UAV.  A shard inserts its own UAVs plus the halo of remote ones near its
+    // bounding box; the table is sized for a halo of up to 3x the shard (a fuller table only means
+    // longer bucket lists, never wrong results)
+    const size_t expect = std::min(ng, std::max<size_t>(4 * size_t(std::max<int64_t>(s.n, 1)), 512));
+    uint32_t     bits   = 10;
+    while ((size_t(1) << bits) < 2 * expect && bits < 30) bits++;
     g.bits      = bits;
     g.n_buckets = 1u << bits;
     CREATE_RC(dalloc(&g.bucket, ng));

@@ -30,6 +30,7 @@
 // Roofline: ~0.4-0.8 kB of state traffic and ~2.6 kFLOP (as-written census) per
 // UAV-step; FP64-pipe bound on B200 once K >= 2, close to balanced at K = 1.
 #include <cstdlib>
+#include <type_traits>
 
 #include "internal.h"
 
@@ -316,6 +317,16 @@ DEV void tma_load(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t
                : "memory");
 }
 
+// 1-D bulk copy shared -> global (local HBM or a peer's, over NVLink) through the TMA unit
+DEV void tma_store(void* gmem_dst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+}
+DEV void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+DEV void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+DEV void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+DEV void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 // where one thread reads its UAV's inputs: tile base + lane, rows 128 doubles apart — either the
 // tile in HBM (direct kernel) or its copy in shared memory (staged kernel)
 struct TileIn {
@@ -328,7 +339,7 @@ struct TileIn {
 // per thread after the last read through `in` (the staged kernel re-arms its TMA there).
 template <int NM_T, int MODE_T, bool ONE, class Hook>
 DEV void step_uav(const DevState& s, const TileIn& in, const int64_t tile, const uint32_t flags0, const int32_t pset, const double dt,
-                  const int k_sub_arg, const int any_moment, Hook after_loads) {
+                  const int k_sub_arg, const int any_moment, double* xyz_stage, Hook after_loads) {
   const int k_sub = ONE ? 1 : k_sub_arg;
   static_assert(MRSB_STEP_THREADS == MRSB_TILE, "one CTA per 128-UAV tile");
   const int64_t i_raw = tile * MRSB_TILE + threadIdx.x;
@@ -734,18 +745,26 @@ DEV void step_uav(const DevState& s, const TileIn& in, const int64_t tile, const
     if (new_flags != flags0) s.flags[i] = new_flags;
     // packed position for the collision pass / the cross-shard all-gather
     const int64_t go = 3 * (s.shard_begin + i);
-    double*       gp = s.gpos + go;
-    gp[0]            = x.x;
-    gp[1]            = x.y;
-    gp[2]            = x.z;
-    if (s.peers) {
-      // fused all-gather: the same 24 bytes go straight into every peer's buffer (posted NVLink stores)
-      for (int r = 0; r < s.n_ranks; r++) {
-        if (r == s.rank) continue;
-        double* pp = s.peers[r] + go;
-        pp[0]      = x.x;
-        pp[1]      = x.y;
-        pp[2]      = x.z;
+    if (xyz_stage) {
+      // staged kernel, full tile: the packed positions of the tile leave through shared memory as
+      // bulk copies to the local gather buffer and to every peer (issued by the caller)
+      xyz_stage[3 * threadIdx.x + 0] = x.x;
+      xyz_stage[3 * threadIdx.x + 1] = x.y;
+      xyz_stage[3 * threadIdx.x + 2] = x.z;
+    } else {
+      double* gp = s.gpos + go;
+      gp[0]      = x.x;
+      gp[1]      = x.y;
+      gp[2]      = x.z;
+      if (s.peers) {
+        // fused all-gather: the same 24 bytes go straight into every peer's buffer (posted NVLink stores)
+        for (int r = 0; r < s.n_ranks; r++) {
+          if (r == s.rank) continue;
+          double* pp = s.peers[r] + go;
+          pp[0]      = x.x;
+          pp[1]      = x.y;
+          pp[2]      = x.z;
+        }
       }
     }
   }
@@ -764,7 +783,7 @@ __global__ void __launch_bounds__(MRSB_STEP_THREADS, MRSB_STEP_MINB) uav_step_ke
   in.cmd  = s.cmd + (tile * CMD_ROWS) * MRSB_TILE + threadIdx.x;
   in.fext = s.fext + (tile * F3_ROWS) * MRSB_TILE + threadIdx.x;
   const int64_t i = min(tile * MRSB_TILE + threadIdx.x, s.n - 1);
-  step_uav<NM_T, MODE_T, ONE>(s, in, tile, s.flags[i], s.pset[s.shard_begin + i], dt, k_sub, any_moment, [] {});
+  step_uav<NM_T, MODE_T, ONE>(s, in, tile, s.flags[i], s.pset[s.shard_begin + i], dt, k_sub, any_moment, nullptr, [] {});
 }
 
 // ---- staged kernel: persistent CTAs, the NEXT tile's inputs are fetched by the TMA unit into
@@ -795,9 +814,11 @@ DEV void stage_tile(const DevState& s, double* sm, uint64_t* bar, int64_t tile) 
   tma_load(sm + SM_FEXT * MRSB_TILE, s.fext + (tile * F3_ROWS) * MRSB_TILE, kRow * F3_ROWS, bar);
 }
 
-template <int NM_T, int MODE_T, bool ONE>
+// BULK: the shard has peers — the tile's packed positions leave through shared memory as TMA bulk
+// stores to the local gather buffer and to every peer's (fused all-gather over NVLink).
+template <int NM_T, int MODE_T, bool ONE, bool BULK>
 __global__ void __launch_bounds__(MRSB_STEP_THREADS, MRSB_STEP_MINB) uav_step_staged_kernel(DevState s, double dt, int k_sub, int any_moment, int64_t n_tiles) {
-  extern __shared__ __align__(128) double sm[];  // SM_ROWS x 128 doubles
+  extern __shared__ __align__(128) double sm[];  // SM_ROWS x 128 doubles (tile image) + 2 x 3 x 128 (outgoing positions)
   __shared__ uint64_t bar;
   if (threadIdx.x == 0) mbar_init(&bar, 1);
   __syncthreads();
@@ -810,6 +831,12 @@ __global__ void __launch_bounds__(MRSB_STEP_THREADS, MRSB_STEP_MINB) uav_step_st
   in.cmd  = sm + SM_CMD * MRSB_TILE + threadIdx.x;
   in.fext = sm + SM_FEXT * MRSB_TILE + threadIdx.x;
   uint32_t phase = 0;
+  // packed positions of a tile (128 x 24 B) leave through two alternating staging buffers
+  double* const xyz_out  = sm + SM_ROWS * MRSB_TILE;
+  // only when there are peers to feed (a single shard stores its 24 bytes per UAV directly: measured
+  // faster than the extra barrier); needs 16-byte alignment of every tile's slice of the gather buffer
+  const bool    bulk_ok  = BULK && s.peers != nullptr && (s.shard_begin & 1) == 0;
+  uint32_t      out_slot = 0;
   // the two per-UAV words that are not part of the tile image are prefetched one tile ahead
   int64_t  i0        = min(tile * MRSB_TILE + threadIdx.x, s.n - 1);
   uint32_t flags_cur = tile < n_tiles ? s.flags[i0] : 0u;
@@ -823,15 +850,35 @@ __global__ void __launch_bounds__(MRSB_STEP_THREADS, MRSB_STEP_MINB) uav_step_st
       flags_next        = s.flags[in_];
       pset_next         = s.pset[s.shard_begin + in_];
     }
+    const bool full  = BULK && bulk_ok && (tile + 1) * MRSB_TILE <= s.n;  // partial last tile: plain stores
+    double*    stage = (BULK && full) ? xyz_out + out_slot * (3 * MRSB_TILE) : nullptr;
     mbar_wait(&bar, phase);
     phase ^= 1u;
-    step_uav<NM_T, MODE_T, ONE>(s, in, tile, flags_cur, pset_cur, dt, k_sub, any_moment, [&] {
+    step_uav<NM_T, MODE_T, ONE>(s, in, tile, flags_cur, pset_cur, dt, k_sub, any_moment, stage, [&] {
+      if (BULK && threadIdx.x == 0) tma_store_wait_read<1>();  // the staging buffer about to be refilled has been read out
       __syncthreads();  // every lane has its inputs in registers: the image may be overwritten
       if (threadIdx.x == 0 && next < n_tiles) stage_tile<NM_T, MODE_T>(s, sm, &bar, next);
     });
+    if (BULK && full) {
+      fence_async_smem();
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        constexpr uint32_t kBytes = 3 * MRSB_TILE * sizeof(double);
+        const int64_t      go     = 3 * (s.shard_begin + tile * MRSB_TILE);
+        tma_store(s.gpos + go, stage, kBytes);
+        if (s.peers) {
+          // fused all-gather: the tile's positions go to every peer's buffer over NVLink as bulk copies
+          for (int r = 0; r < s.n_ranks; r++)
+            if (r != s.rank) tma_store(s.peers[r] + go, stage, kBytes);
+        }
+        tma_store_commit();
+      }
+      out_slot ^= 1u;
+    }
     flags_cur = flags_next;
     pset_cur  = pset_next;
   }
+  if (BULK && threadIdx.x == 0) tma_store_wait_all();
 }
 
 __global__ void publish_positions_kernel(DevState s) {
@@ -844,11 +891,11 @@ __global__ void publish_positions_kernel(DevState s) {
 }
 
 // CTAs of the staged kernel that fit on the device (persistent grid), cached per instantiation
-template <int NM_T, int MODE_T, bool ONE>
+template <int NM_T, int MODE_T, bool ONE, bool BULK>
 int staged_grid(size_t smem) {
   static int cached = -1;
   if (cached < 0) {
-    auto* k = uav_step_staged_kernel<NM_T, MODE_T, ONE>;
+    auto* k = uav_step_staged_kernel<NM_T, MODE_T, ONE, BULK>;
     if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess) {
       cudaGetLastError();
       cached = 0;
@@ -870,15 +917,21 @@ void launch_one(const DevState& s, double dt, int k, int any_moment, cudaStream_
   if constexpr (NM_T > 0 && MODE_T >= 0) {
     // enough tiles to fill the machine more than once: persistent CTAs + TMA staging hide the HBM
     // latency behind the integration of the previous tile
-    const size_t smem = size_t(SM_ROWS) * MRSB_TILE * sizeof(double);
-    const int    grid = (k == 1) ? staged_grid<NM_T, MODE_T, true>(smem) : staged_grid<NM_T, MODE_T, false>(smem);
-    if (grid > 0 && n_tiles > grid && !getenv("MRSB_NO_STAGING")) {
-      if (k == 1) {
-        uav_step_staged_kernel<NM_T, MODE_T, true><<<grid, threads, smem, st>>>(s, dt, k, any_moment, n_tiles);
-      } else {
-        uav_step_staged_kernel<NM_T, MODE_T, false><<<grid, threads, smem, st>>>(s, dt, k, any_moment, n_tiles);
-      }
-      return;
+    const bool   bulk = s.peers != nullptr;
+    const size_t smem = (size_t(SM_ROWS) + (bulk ? 6 : 0)) * MRSB_TILE * sizeof(double);  // tile image (+ two xyz staging buffers)
+    auto launch = [&](auto one, auto blk) -> bool {
+      constexpr bool kOne = decltype(one)::value, kBulk = decltype(blk)::value;
+      const int      grid = staged_grid<NM_T, MODE_T, kOne, kBulk>(smem);
+      if (grid <= 0 || n_tiles <= grid) return false;
+      uav_step_staged_kernel<NM_T, MODE_T, kOne, kBulk><<<grid, threads, smem, st>>>(s, dt, k, any_moment, n_tiles);
+      return true;
+    };
+    if (!getenv("MRSB_NO_STAGING")) {
+      // enough tiles to fill the machine more than once: persistent CTAs + TMA staging hide the HBM
+      // latency behind the integration of the previous tile
+      const bool done = (k == 1) ? (bulk ? launch(std::true_type{}, std::true_type{}) : launch(std::true_type{}, std::false_type{}))
+                                 : (bulk ? launch(std::false_type{}, std::true_type{}) : launch(std::false_type{}, std::false_type{}));
+      if (done) return;
     }
   }
   if (k == 1) {
