@@ -110,6 +110,8 @@ struct mrsb_sim {
 
   int  uniform_mode = MRSB_INPUT_UNKNOWN;  // INPUT_MODE shared by all UAVs, or -1 if mixed
   int  uniform_nm   = 0;                   // n_motors shared by all local UAVs, or 0 if mixed
+  int  uniform_pset = -1;                  // parameter set shared by all local UAVs, or -1 if mixed
+  DevParams uniform_params{};              // host copy of that set (goes to the kernel by value)
   bool any_moment   = false;
 
   int    coll_enabled = 0, coll_crash = 0;
@@ -201,16 +203,19 @@ static int flush_params(mrsb_sim* h) {
   for (int k = 0; k < n_sets; k++) mrsb_derive(h->sets[k].mp, h->sets[k].cp, &host[k]);
   CU(cudaMemcpyAsync(h->d_params, host.data(), sizeof(DevParams) * n_sets, cudaMemcpyHostToDevice, h->stream));
   CU(cudaStreamSynchronize(h->stream));  // `host` goes out of scope
-  int nm = -1;
+  int nm = -1, ps = -2;
   for (int64_t i = 0; i < h->ds.n; i++) {
-    const int m = h->sets[h->pset_host[h->ds.shard_begin + i]].mp.n_motors;
+    const int id = h->pset_host[h->ds.shard_begin + i];
+    const int m  = h->sets[id].mp.n_motors;
     if (nm == -1) nm = m;
-    if (nm != m) {
-      nm = 0;
-      break;
-    }
+    if (nm != m) nm = 0;
+    if (ps == -2) ps = id;
+    if (ps != id) ps = -1;
+    if (nm == 0 && ps == -1) break;
   }
   h->uniform_nm   = nm > 0 ? nm : 0;
+  h->uniform_pset = ps >= 0 ? ps : -1;
+  if (h->uniform_pset >= 0) h->uniform_params = host[size_t(h->uniform_pset)];
   h->params_dirty = false;
   return MRSB_OK;
 }
@@ -813,7 +818,8 @@ int mrsb_make_step(mrsb_handle h, double dt, int32_t k_substeps) {
     h->epoch++;
     h->pushed = true;
   }
-  h->n_launches += launch_step(h->ds, dt, k_substeps, h->uniform_mode, h->uniform_nm, h->any_moment, h->stream);
+  h->n_launches += launch_step(h->ds, h->uniform_pset >= 0 ? &h->uniform_params : nullptr, dt, k_substeps, h->uniform_mode, h->uniform_nm,
+                               h->any_moment, h->stream);
   h->n_steps += k_substeps;
   CU(cudaGetLastError());
   return MRSB_OK;

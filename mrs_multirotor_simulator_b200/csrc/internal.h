@@ -110,7 +110,9 @@ struct DevGrid {
 };
 
 // kernel launchers (step_kernel.cu / collide.cu / io_kernels.cu); all return the number of launches made
-int launch_step(const DevState& s, double dt, int k_substeps, int uniform_mode, int uniform_nm, bool any_moment, cudaStream_t stream);
+// uniform_params: host copy of THE parameter set when every local UAV uses the same one, else nullptr
+int launch_step(const DevState& s, const DevParams* uniform_params, double dt, int k_substeps, int uniform_mode, int uniform_nm, bool any_moment,
+                cudaStream_t stream);
 int launch_collide(const DevState& s, const DevGrid& g, int crash_mode, double rebounce, void* cub_tmp, size_t cub_tmp_bytes, cudaStream_t stream);
 size_t collide_tmp_bytes(int64_t n_global);
 int launch_publish_positions(const DevState& s, cudaStream_t stream);

@@ -338,8 +338,11 @@ struct TileIn {
 // speeds are dead after their single use, which is worth ~60 registers).  `after_loads` runs once
 // per thread after the last read through `in` (the staged kernel re-arms its TMA there).
 template <int NM_T, int MODE_T, bool ONE, class Hook>
-DEV void step_uav(const DevState& s, const TileIn& in, const int64_t tile, const uint32_t flags0, const int32_t pset, const double dt,
-                  const int k_sub_arg, const int any_moment, double* xyz_stage, Hook after_loads) {
+DEV void step_uav(const DevState& s, const TileIn& in, const int64_t tile, const uint32_t flags0, const DevParams* batch_params, const int32_t pset,
+                  const double dt, const int k_sub_arg, const int any_moment, double* xyz_stage, Hook after_loads) {
+  // batch_params: the whole batch's single parameter set in the constant bank (staged kernel), or
+  // nullptr -> this UAV's entry of the table in HBM (read-only path)
+  const DevParams* __restrict__ P = batch_params ? batch_params : s.params + pset;
   const int k_sub = ONE ? 1 : k_sub_arg;
   static_assert(MRSB_STEP_THREADS == MRSB_TILE, "one CTA per 128-UAV tile");
   const int64_t i_raw = tile * MRSB_TILE + threadIdx.x;
@@ -359,7 +362,6 @@ DEV void step_uav(const DevState& s, const TileIn& in, const int64_t tile, const
   const double* const t_mext  = s.mext + (tile * F3_ROWS) * MRSB_TILE + threadIdx.x;
   const double* const t_vprev = s.vprev + (tile * VPREV_ROWS) * MRSB_TILE + threadIdx.x;
 
-  const DevParams* __restrict__ P = s.params + pset;
   const int nm                    = NM_T > 0 ? NM_T : P->n_motors;
   const int mode0                 = MODE_T >= 0 ? MODE_T : int(s.mode[i]);
   uint32_t flags                  = flags0;
@@ -783,7 +785,7 @@ __global__ void __launch_bounds__(MRSB_STEP_THREADS, MRSB_STEP_MINB) uav_step_ke
   in.cmd  = s.cmd + (tile * CMD_ROWS) * MRSB_TILE + threadIdx.x;
   in.fext = s.fext + (tile * F3_ROWS) * MRSB_TILE + threadIdx.x;
   const int64_t i = min(tile * MRSB_TILE + threadIdx.x, s.n - 1);
-  step_uav<NM_T, MODE_T, ONE>(s, in, tile, s.flags[i], s.pset[s.shard_begin + i], dt, k_sub, any_moment, nullptr, [] {});
+  step_uav<NM_T, MODE_T, ONE>(s, in, tile, s.flags[i], nullptr, s.pset[s.shard_begin + i], dt, k_sub, any_moment, nullptr, [] {});
 }
 
 // ---- staged kernel: persistent CTAs, the NEXT tile's inputs are fetched by the TMA unit into
@@ -817,7 +819,10 @@ DEV void stage_tile(const DevState& s, double* sm, uint64_t* bar, int64_t tile) 
 // BULK: the shard has peers — the tile's packed positions leave through shared memory as TMA bulk
 // stores to the local gather buffer and to every peer's (fused all-gather over NVLink).
 template <int NM_T, int MODE_T, bool ONE, bool BULK>
-__global__ void __launch_bounds__(MRSB_STEP_THREADS, MRSB_STEP_MINB) uav_step_staged_kernel(DevState s, double dt, int k_sub, int any_moment, int64_t n_tiles) {
+__global__ void __launch_bounds__(MRSB_STEP_THREADS, MRSB_STEP_MINB)
+    uav_step_staged_kernel(DevState s, const __grid_constant__ DevParams params, double dt, int k_sub, int any_moment, int64_t n_tiles) {
+  // `params`: the one parameter set of the whole batch, passed BY VALUE: it lives in the constant
+  // bank, so airframe constants and gains are instruction operands instead of ~80 loads per UAV
   extern __shared__ __align__(128) double sm[];  // SM_ROWS x 128 doubles (tile image) + 2 x 3 x 128 (outgoing positions)
   __shared__ uint64_t bar;
   if (threadIdx.x == 0) mbar_init(&bar, 1);
@@ -837,24 +842,18 @@ __global__ void __launch_bounds__(MRSB_STEP_THREADS, MRSB_STEP_MINB) uav_step_st
   // faster than the extra barrier); needs 16-byte alignment of every tile's slice of the gather buffer
   const bool    bulk_ok  = BULK && s.peers != nullptr && (s.shard_begin & 1) == 0;
   uint32_t      out_slot = 0;
-  // the two per-UAV words that are not part of the tile image are prefetched one tile ahead
+  // the per-UAV word that is not part of the tile image is prefetched one tile ahead
   int64_t  i0        = min(tile * MRSB_TILE + threadIdx.x, s.n - 1);
   uint32_t flags_cur = tile < n_tiles ? s.flags[i0] : 0u;
-  int32_t  pset_cur  = tile < n_tiles ? s.pset[s.shard_begin + i0] : 0;
   for (; tile < n_tiles; tile += gridDim.x) {
     const int64_t next = tile + gridDim.x;
     uint32_t      flags_next = 0u;
-    int32_t       pset_next  = 0;
-    if (next < n_tiles) {
-      const int64_t in_ = min(next * MRSB_TILE + threadIdx.x, s.n - 1);
-      flags_next        = s.flags[in_];
-      pset_next         = s.pset[s.shard_begin + in_];
-    }
+    if (next < n_tiles) flags_next = s.flags[min(next * MRSB_TILE + threadIdx.x, s.n - 1)];
     const bool full  = BULK && bulk_ok && (tile + 1) * MRSB_TILE <= s.n;  // partial last tile: plain stores
     double*    stage = (BULK && full) ? xyz_out + out_slot * (3 * MRSB_TILE) : nullptr;
     mbar_wait(&bar, phase);
     phase ^= 1u;
-    step_uav<NM_T, MODE_T, ONE>(s, in, tile, flags_cur, pset_cur, dt, k_sub, any_moment, stage, [&] {
+    step_uav<NM_T, MODE_T, ONE>(s, in, tile, flags_cur, &params, 0, dt, k_sub, any_moment, stage, [&] {
       if (BULK && threadIdx.x == 0) tma_store_wait_read<1>();  // the staging buffer about to be refilled has been read out
       __syncthreads();  // every lane has its inputs in registers: the image may be overwritten
       if (threadIdx.x == 0 && next < n_tiles) stage_tile<NM_T, MODE_T>(s, sm, &bar, next);
@@ -876,7 +875,6 @@ __global__ void __launch_bounds__(MRSB_STEP_THREADS, MRSB_STEP_MINB) uav_step_st
       out_slot ^= 1u;
     }
     flags_cur = flags_next;
-    pset_cur  = pset_next;
   }
   if (BULK && threadIdx.x == 0) tma_store_wait_all();
 }
@@ -911,10 +909,10 @@ int staged_grid(size_t smem) {
 }
 
 template <int NM_T, int MODE_T>
-void launch_one(const DevState& s, double dt, int k, int any_moment, cudaStream_t st) {
+void launch_one(const DevState& s, const DevParams* uniform_params, double dt, int k, int any_moment, cudaStream_t st) {
   const int     threads = MRSB_STEP_THREADS;
   const int64_t n_tiles = (s.n + threads - 1) / threads;
-  if constexpr (NM_T > 0 && MODE_T >= 0) {
+  if constexpr (NM_T > 0 && MODE_T >= 0) if (uniform_params) {
     // enough tiles to fill the machine more than once: persistent CTAs + TMA staging hide the HBM
     // latency behind the integration of the previous tile
     const bool   bulk = s.peers != nullptr;
@@ -923,7 +921,7 @@ void launch_one(const DevState& s, double dt, int k, int any_moment, cudaStream_
       constexpr bool kOne = decltype(one)::value, kBulk = decltype(blk)::value;
       const int      grid = staged_grid<NM_T, MODE_T, kOne, kBulk>(smem);
       if (grid <= 0 || n_tiles <= grid) return false;
-      uav_step_staged_kernel<NM_T, MODE_T, kOne, kBulk><<<grid, threads, smem, st>>>(s, dt, k, any_moment, n_tiles);
+      uav_step_staged_kernel<NM_T, MODE_T, kOne, kBulk><<<grid, threads, smem, st>>>(s, *uniform_params, dt, k, any_moment, n_tiles);
       return true;
     };
     if (!getenv("MRSB_NO_STAGING")) {
@@ -942,42 +940,43 @@ void launch_one(const DevState& s, double dt, int k, int any_moment, cudaStream_
 }
 
 template <int NM_T>
-void launch_nm(const DevState& s, double dt, int k, int mode, int any_moment, cudaStream_t st) {
+void launch_nm(const DevState& s, const DevParams* up, double dt, int k, int mode, int any_moment, cudaStream_t st) {
   switch (mode) {
     case MRSB_ACTUATOR_CMD:
-      launch_one<NM_T, MRSB_ACTUATOR_CMD>(s, dt, k, any_moment, st);
+      launch_one<NM_T, MRSB_ACTUATOR_CMD>(s, up, dt, k, any_moment, st);
       break;
     case MRSB_VELOCITY_HDG_RATE_CMD:
-      launch_one<NM_T, MRSB_VELOCITY_HDG_RATE_CMD>(s, dt, k, any_moment, st);
+      launch_one<NM_T, MRSB_VELOCITY_HDG_RATE_CMD>(s, up, dt, k, any_moment, st);
       break;
     case MRSB_VELOCITY_HDG_CMD:
-      launch_one<NM_T, MRSB_VELOCITY_HDG_CMD>(s, dt, k, any_moment, st);
+      launch_one<NM_T, MRSB_VELOCITY_HDG_CMD>(s, up, dt, k, any_moment, st);
       break;
     case MRSB_POSITION_CMD:
-      launch_one<NM_T, MRSB_POSITION_CMD>(s, dt, k, any_moment, st);
+      launch_one<NM_T, MRSB_POSITION_CMD>(s, up, dt, k, any_moment, st);
       break;
     default:
-      launch_one<NM_T, -1>(s, dt, k, any_moment, st);
+      launch_one<NM_T, -1>(s, up, dt, k, any_moment, st);
       break;
   }
 }
 
 }  // namespace
 
-int launch_step(const DevState& s, double dt, int k_substeps, int uniform_mode, int uniform_nm, bool any_moment, cudaStream_t stream) {
+int launch_step(const DevState& s, const DevParams* uniform_params, double dt, int k_substeps, int uniform_mode, int uniform_nm, bool any_moment,
+                cudaStream_t stream) {
   if (s.n <= 0) return 0;
   switch (uniform_nm) {
     case 4:
-      launch_nm<4>(s, dt, k_substeps, uniform_mode, any_moment, stream);
+      launch_nm<4>(s, uniform_params, dt, k_substeps, uniform_mode, any_moment, stream);
       break;
     case 6:
-      launch_nm<6>(s, dt, k_substeps, uniform_mode, any_moment, stream);
+      launch_nm<6>(s, uniform_params, dt, k_substeps, uniform_mode, any_moment, stream);
       break;
     case 8:
-      launch_nm<8>(s, dt, k_substeps, uniform_mode, any_moment, stream);
+      launch_nm<8>(s, uniform_params, dt, k_substeps, uniform_mode, any_moment, stream);
       break;
     default:
-      launch_nm<0>(s, dt, k_substeps, uniform_mode, any_moment, stream);
+      launch_nm<0>(s, uniform_params, dt, k_substeps, uniform_mode, any_moment, stream);
       break;
   }
   return 1;
