@@ -144,8 +144,20 @@ struct mrsb_sim {
   cudaEvent_t  ev_up[2] = {nullptr, nullptr}, ev_applied[2] = {nullptr, nullptr}, ev_snap[2] = {nullptr, nullptr}, ev_down[2] = {nullptr, nullptr};
   uint64_t     n_up = 0, n_down = 0;
 
+  // the collision pass is a fixed sequence of 7 launches with fixed arguments: replayed as a CUDA graph
+  // (one per gather-buffer parity); invalidated when its arguments change
+  cudaGraphExec_t coll_graph[2]     = {nullptr, nullptr};
+  int             coll_graph_own[2] = {0, 0};  // own kernels per replay (for the launch counter)
+
   int64_t n_steps = 0, n_passes = 0, n_launches = 0;
 };
+
+static void drop_collision_graphs(mrsb_sim* h) {
+  for (int k = 0; k < 2; k++) {
+    if (h->coll_graph[k]) cudaGraphExecDestroy(h->coll_graph[k]);
+    h->coll_graph[k] = nullptr;
+  }
+}
 
 static std::string set_key(const ParamSet& s) {
   return std::string(reinterpret_cast<const char*>(&s), sizeof(ParamSet));
@@ -198,6 +210,7 @@ static int flush_params(mrsb_sim* h) {
     h->d_params_cap = std::max(16, 2 * n_sets);
     CU(cudaMalloc(&h->d_params, sizeof(DevParams) * h->d_params_cap));
     h->ds.params = h->d_params;
+    drop_collision_graphs(h);
   }
   std::vector<DevParams> host(n_sets);
   for (int k = 0; k < n_sets; k++) mrsb_derive(h->sets[k].mp, h->sets[k].cp, &host[k]);
@@ -380,6 +393,7 @@ static int setup_p2p(mrsb_sim* h) {
   h->parity   = 0;
   h->ds.peers = nullptr;  // set per step
   h->p2p      = true;
+  drop_collision_graphs(h);
   return MRSB_OK;
 }
 
@@ -409,6 +423,7 @@ int mrsb_destroy(mrsb_handle h) {
   }
   if (h->up_stream) cudaStreamDestroy(h->up_stream);
   if (h->down_stream) cudaStreamDestroy(h->down_stream);
+  drop_collision_graphs(h);
   for (void* p : h->ipc_opened) cudaIpcCloseMemHandle(p);
   if (h->gbuf[1] && h->gbuf[1] != h->ds.gpos) cudaFree(h->gbuf[1]);
   if (h->gbuf[0] && h->gbuf[0] != h->ds.gpos) cudaFree(h->gbuf[0]);
@@ -799,7 +814,25 @@ static int exchange_positions(mrsb_sim* h) {
 }
 
 static int collide_local(mrsb_sim* h) {
-  h->n_launches += launch_collide(h->ds, h->grid, h->coll_crash, h->coll_rebounce, h->cub_tmp, h->cub_tmp_bytes, h->stream);
+  const int k = h->p2p ? h->parity : 0;
+  if (!h->coll_graph[k] && !getenv("MRSB_NO_GRAPH")) {
+    cudaGraph_t graph = nullptr;
+    if (cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+      const int own = launch_collide(h->ds, h->grid, h->coll_crash, h->coll_rebounce, h->cub_tmp, h->cub_tmp_bytes, h->stream);
+      if (cudaStreamEndCapture(h->stream, &graph) == cudaSuccess && graph) {
+        if (cudaGraphInstantiate(&h->coll_graph[k], graph, 0) != cudaSuccess) h->coll_graph[k] = nullptr;
+        cudaGraphDestroy(graph);
+        h->coll_graph_own[k] = own;
+      }
+    }
+    cudaGetLastError();
+  }
+  if (h->coll_graph[k]) {
+    CU(cudaGraphLaunch(h->coll_graph[k], h->stream));
+    h->n_launches += h->coll_graph_own[k];
+  } else {
+    h->n_launches += launch_collide(h->ds, h->grid, h->coll_crash, h->coll_rebounce, h->cub_tmp, h->cub_tmp_bytes, h->stream);
+  }
   h->n_passes++;
   CU(cudaGetLastError());
   return MRSB_OK;
@@ -1103,6 +1136,7 @@ int mrsb_set_collisions(mrsb_handle h, int32_t enabled, int32_t crash, double re
   h->coll_enabled  = enabled != 0;
   h->coll_crash    = crash != 0;
   h->coll_rebounce = rebounce;
+  drop_collision_graphs(h);
   return MRSB_OK;
 }
 
@@ -1138,6 +1172,7 @@ int mrsb_set_pair_capacity(mrsb_handle h, int64_t max_pairs) {
   if (h->grid.pairs) CU(cudaFree(h->grid.pairs));
   h->grid.pairs    = fresh;
   h->grid.pair_cap = max_pairs;
+  drop_collision_graphs(h);
   CU(cudaMemsetAsync(h->grid.counters, 0, sizeof(unsigned long long), h->stream));
   return MRSB_OK;
 }

@@ -147,7 +147,10 @@ DEV double nf_dist2(double ax, double ay, double az, double bx, double by, doubl
   return r;
 }
 
-__global__ void __launch_bounds__(128) collide_kernel(DevState s, DevGrid g, int crash_mode, double rebounce) {
+#ifndef MRSB_COLLIDE_MINB
+#define MRSB_COLLIDE_MINB 7  // 71 registers, no spills; 8 and 10 (64 / 48 registers) measured no faster
+#endif
+__global__ void __launch_bounds__(128, MRSB_COLLIDE_MINB) collide_kernel(DevState s, DevGrid g, int crash_mode, double rebounce) {
   const int64_t p = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (p >= int64_t(g.begin[g.n_buckets])) return;  // beyond the primary records (the mirror bucket holds copies)
   const double4 q  = g.rec[p];
