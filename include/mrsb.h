@@ -249,6 +249,27 @@ int mrsb_get_controller_params(mrsb_handle h, int64_t uav, mrsb_controller_param
  * row-major [n_motors][4] written into out[MRSB_MAX_MOTORS*4]. */
 int mrsb_get_mixer_allocation(mrsb_handle h, int64_t uav, double* out);
 
+/* ---- the ROS wrapper's arithmetic around the path (src/uav_system_ros.cpp), batched -------------
+ * mrsb_timeout_input: UavSystemRos::timeoutInput (ROSW:474-647) — replace the active command by its
+ *   hover version (Position: hold the current position and heading; Velocity / Acceleration: zero;
+ *   Attitude: level at the current heading, zero throttle; ...); the caller decides WHEN (the
+ *   reference: no command for `input_timeout` seconds, ROSW:247-261).
+ * mrsb_get_odometry:    publishOdometry (ROSW:340-368), rows [13]: position xyz, orientation
+ *   quaternion xyzw (Eigen::Quaterniond(R)), linear velocity in the BODY frame (R^T v), angular velocity.
+ * mrsb_get_imu:         publishIMU (ROSW:374-395), rows [10]: angular velocity, linear acceleration, orientation xyzw.
+ * mrsb_get_rangefinder: publishRangefinder (ROSW:401-420), rows [1]: (z - ground_z)/cos(tilt) + 0.01, 41.0 beyond 40 m or when inverted.
+ * mrsb_pack_observations_device: all of it for every UAV into a DEVICE buffer, rows [stride >= 17]:
+ *   odometry 13 | IMU linear acceleration 3 | range 1 (enqueued on the handle's stream, no host round trip).
+ * mrsb_set_mass / mrsb_set_ground_z: the set_mass / set_ground_z services (ROSW:1028-1080): like the
+ *   reference they go through setParams, i.e. controllers return to default gains and PIDs reset. */
+int mrsb_timeout_input(mrsb_handle h, int64_t n, const int32_t* idx);
+int mrsb_get_odometry(mrsb_handle h, int64_t n, const int32_t* idx, double* out13);
+int mrsb_get_imu(mrsb_handle h, int64_t n, const int32_t* idx, double* out10);
+int mrsb_get_rangefinder(mrsb_handle h, int64_t n, const int32_t* idx, double* out1);
+int mrsb_pack_observations_device(mrsb_handle h, double* out_dev, int32_t stride);
+int mrsb_set_mass(mrsb_handle h, int64_t n, const int32_t* idx, const double* mass);
+int mrsb_set_ground_z(mrsb_handle h, int64_t n, const int32_t* idx, const double* ground_z);
+
 /* ---- collisions: MultirotorSimulator::handleCollisions (SIM:295-359) -----------------------
  * knobs = collisions/enabled, collisions/crash, collisions/rebounce (SIM:124-126,
  * cfg/multirotor_simulator.cfg:12-20).  The pass runs on the CURRENT positions: uniform-grid

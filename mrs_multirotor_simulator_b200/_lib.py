@@ -103,6 +103,13 @@ SIGNATURES = {
     "mrsb_set_position_controller_params": (C.c_int, _N_IDX + [C.c_double] * 4),
     "mrsb_get_controller_params": (C.c_int, [H, C.c_int64, C.POINTER(ControllerParams)]),
     "mrsb_get_mixer_allocation": (C.c_int, [H, C.c_int64, C.c_void_p]),
+    "mrsb_timeout_input": (C.c_int, _N_IDX),
+    "mrsb_get_odometry": (C.c_int, _N_IDX + [C.c_void_p]),
+    "mrsb_get_imu": (C.c_int, _N_IDX + [C.c_void_p]),
+    "mrsb_get_rangefinder": (C.c_int, _N_IDX + [C.c_void_p]),
+    "mrsb_pack_observations_device": (C.c_int, [H, C.c_void_p, C.c_int32]),
+    "mrsb_set_mass": (C.c_int, _N_IDX + [C.c_void_p]),
+    "mrsb_set_ground_z": (C.c_int, _N_IDX + [C.c_void_p]),
     "mrsb_set_collisions": (C.c_int, [H, C.c_int32, C.c_int32, C.c_double]),
     "mrsb_handle_collisions": (C.c_int, [H]),
     "mrsb_get_collision_pairs": (C.c_int, [H, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]),

@@ -251,6 +251,44 @@ class UavBatch:
         check(self._L.mrsb_get_mixer_allocation(self.h, uav, _ptr(out)))
         return out
 
+    # ---- the ROS wrapper's arithmetic around the path (uav_system_ros.cpp) -------------------------
+    def timeout_input(self, idx=None):
+        """UavSystemRos::timeoutInput (uav_system_ros.cpp:474-647): the active command becomes its hover version."""
+        idx = _idx(idx)
+        check(self._L.mrsb_timeout_input(self.h, self._n(idx), _ptr(idx)))
+
+    def _rows(self, fn, width, idx):
+        idx = _idx(idx)
+        out = np.empty((self._n(idx), width))
+        check(getattr(self._L, fn)(self.h, len(out), _ptr(idx), _ptr(out)))
+        return out
+
+    def get_odometry(self, idx=None):
+        """rows [13]: position, orientation xyzw, body-frame linear velocity, angular velocity (uav_system_ros.cpp:340-368)."""
+        return self._rows("mrsb_get_odometry", 13, idx)
+
+    def get_imu(self, idx=None):
+        """rows [10]: angular velocity, linear acceleration, orientation xyzw (uav_system_ros.cpp:374-395)."""
+        return self._rows("mrsb_get_imu", 10, idx)
+
+    def get_rangefinder(self, idx=None):
+        """rows [1]: down-looking range (uav_system_ros.cpp:401-420)."""
+        return self._rows("mrsb_get_rangefinder", 1, idx)
+
+    def pack_observations_device(self, out_ptr, stride=17):
+        """odometry 13 | IMU acceleration 3 | range 1 for every UAV into a device buffer (no host round trip)."""
+        check(self._L.mrsb_pack_observations_device(self.h, out_ptr, stride))
+
+    def set_mass(self, mass, idx=None):
+        idx = _idx(idx)
+        m = np.ascontiguousarray(np.broadcast_to(mass, (self._n(idx),)), dtype=np.float64)
+        check(self._L.mrsb_set_mass(self.h, len(m), _ptr(idx), _ptr(m)))
+
+    def set_ground_z(self, z, idx=None):
+        idx = _idx(idx)
+        z = np.ascontiguousarray(np.broadcast_to(z, (self._n(idx),)), dtype=np.float64)
+        check(self._L.mrsb_set_ground_z(self.h, len(z), _ptr(idx), _ptr(z)))
+
     # ---- collisions -----------------------------------------------------------------------------
     def set_collisions(self, enabled, crash, rebounce):
         check(self._L.mrsb_set_collisions(self.h, int(bool(enabled)), int(bool(crash)), float(rebounce)))

@@ -8,6 +8,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <string>
 #include <vector>
@@ -1126,6 +1127,95 @@ int mrsb_set_position_controller_params(mrsb_handle h, int64_t n, const int32_t*
   return set_ctrl(h, n, idx, 0, 6, [](ParamSet& s, const double* v) {
     s.cp.pos_kp = v[0], s.cp.pos_kd = v[1], s.cp.pos_ki = v[2], s.cp.pos_max_velocity = v[3];
   }, v);
+}
+
+// ------------------------------------------------------------------------------------------
+// ROS-wrapper arithmetic around the path
+// ------------------------------------------------------------------------------------------
+int mrsb_timeout_input(mrsb_handle h, int64_t n, const int32_t* idx) {
+  GUARD(h);
+  const int32_t* d_idx = nullptr;
+  int            rc    = stage_idx(h, n, idx, &d_idx);
+  if (rc) return rc;
+  h->n_launches += launch_timeout_input(h->ds, n, d_idx, h->stream);
+  CU(cudaGetLastError());
+  return MRSB_OK;
+}
+
+static int observe(mrsb_sim* h, int what, int width, int64_t n, const int32_t* idx, double* out) {
+  if (!out) return fail(MRSB_ERR_INVALID, "null output");
+  int rc = flush_params(h);
+  if (rc) return rc;
+  const int32_t* d_idx = nullptr;
+  rc                   = stage_idx(h, n, idx, &d_idx);
+  if (rc) return rc;
+  if (n == 0) return MRSB_OK;
+  const size_t bytes = sizeof(double) * size_t(n) * size_t(width);
+  rc                 = ensure_stage(h, bytes);
+  if (rc) return rc;
+  h->n_launches += launch_observe(h->ds, what, n, d_idx, reinterpret_cast<double*>(h->d_stage), width, h->stream);
+  CU(cudaMemcpyAsync(out, h->d_stage, bytes, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return MRSB_OK;
+}
+int mrsb_get_odometry(mrsb_handle h, int64_t n, const int32_t* idx, double* out13) {
+  GUARD(h);
+  return observe(h, 0, 13, n, idx, out13);
+}
+int mrsb_get_imu(mrsb_handle h, int64_t n, const int32_t* idx, double* out10) {
+  GUARD(h);
+  return observe(h, 1, 10, n, idx, out10);
+}
+int mrsb_get_rangefinder(mrsb_handle h, int64_t n, const int32_t* idx, double* out1) {
+  GUARD(h);
+  return observe(h, 2, 1, n, idx, out1);
+}
+int mrsb_pack_observations_device(mrsb_handle h, double* out_dev, int32_t stride) {
+  GUARD(h);
+  if (!out_dev || stride < 17) return fail(MRSB_ERR_INVALID, "need a device buffer with rows of >= 17 doubles");
+  int rc = flush_params(h);
+  if (rc) return rc;
+  h->n_launches += launch_observe(h->ds, 3, h->ds.n, nullptr, out_dev, stride, h->stream);
+  CU(cudaGetLastError());
+  return MRSB_OK;
+}
+
+// set_mass / set_ground_z services: getParams -> edit -> setParams, per UAV (ROSW:1028-1080)
+static int edit_params_each(mrsb_sim* h, int64_t n, const int32_t* idx, const std::function<void(mrsb_model_params&, int64_t)>& edit) {
+  if (n < 0 || (!idx && n > h->ds.n)) return fail(MRSB_ERR_INVALID, "n=%lld outside 0..%lld", (long long)n, (long long)h->ds.n);
+  std::vector<uint32_t> fl;
+  int                   rc = get_flags(h, n, idx, fl);
+  if (rc) return rc;
+  for (int64_t k = 0; k < n; k++) {
+    const int32_t     i = idx ? idx[k] : int32_t(k);
+    mrsb_model_params p = h->sets[h->pset_host[size_t(h->ds.shard_begin + i)]].mp;
+    p.takeoff_patch_enabled = (fl[size_t(k)] & FLAG_TAKEOFF) ? 1 : 0;  // getParams returns the live flag (MM:275)
+    edit(p, k);
+    rc = mrsb_set_params(h, 1, &i, &p);
+    if (rc) return rc;
+  }
+  return MRSB_OK;
+}
+
+int mrsb_set_mass(mrsb_handle h, int64_t n, const int32_t* idx, const double* mass) {
+  GUARD(h);
+  if (!mass && n) return fail(MRSB_ERR_INVALID, "null mass");
+  return edit_params_each(h, n, idx, [&](mrsb_model_params& p, int64_t k) {
+    const double original = p.mass;
+    p.mass                = mass[k];
+    for (int m = 0; m < p.n_motors; m++)
+      p.allocation_matrix[2 * MRSB_MAX_MOTORS + m] = p.mass * (p.allocation_matrix[2 * MRSB_MAX_MOTORS + m] / original);
+    std::memset(p.J, 0, sizeof(p.J));
+    p.J[0] = p.mass * (3.0 * p.arm_length * p.arm_length + p.body_height * p.body_height) / 12.0;
+    p.J[4] = p.mass * (3.0 * p.arm_length * p.arm_length + p.body_height * p.body_height) / 12.0;
+    p.J[8] = (p.mass * p.arm_length * p.arm_length) / 2.0;
+  });
+}
+
+int mrsb_set_ground_z(mrsb_handle h, int64_t n, const int32_t* idx, const double* ground_z) {
+  GUARD(h);
+  if (!ground_z && n) return fail(MRSB_ERR_INVALID, "null ground_z");
+  return edit_params_each(h, n, idx, [&](mrsb_model_params& p, int64_t k) { p.ground_z = ground_z[k]; });
 }
 
 // ------------------------------------------------------------------------------------------

@@ -135,7 +135,127 @@ __global__ void set_pset_kernel(int32_t* __restrict__ pset, int64_t n, const int
   pset[offset + at(idx, k)] = values[k];
 }
 
+// UavSystemRos::timeoutInput (ROSW:474-647): the active command becomes its "hover" version
+__global__ void timeout_input_kernel(DevState s, int64_t n, const int32_t* __restrict__ idx) {
+  const int64_t k = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const int64_t i    = at(idx, k);
+  const int     mode = s.mode[i];
+  auto          C    = [&](int row) -> double& { return s.cmd[tix(CMD_ROWS, row, i)]; };
+  auto          S    = [&](int row) { return s.st[tix(ST_ROWS, row, i)]; };
+  const double  hdg  = atan2(S(7), S(6));  // AttitudeConverter(R).getHeading(): atan2(R10, R00)
+  double        sh, ch;
+  sincos(hdg, &sh, &ch);
+  switch (mode) {
+    case MRSB_POSITION_CMD:
+      C(0) = S(0), C(1) = S(1), C(2) = S(2), C(3) = hdg, C(CMD_COS) = ch, C(CMD_SIN) = sh;
+      break;
+    case MRSB_VELOCITY_HDG_CMD:
+    case MRSB_ACCELERATION_HDG_CMD:
+      C(0) = 0.0, C(1) = 0.0, C(2) = 0.0, C(3) = hdg, C(CMD_COS) = ch, C(CMD_SIN) = sh;
+      break;
+    case MRSB_VELOCITY_HDG_RATE_CMD:
+    case MRSB_ACCELERATION_HDG_RATE_CMD:
+    case MRSB_ATTITUDE_RATE_CMD:
+    case MRSB_CONTROL_GROUP_CMD:
+      C(0) = 0.0, C(1) = 0.0, C(2) = 0.0, C(3) = 0.0;
+      break;
+    case MRSB_ATTITUDE_CMD:  // AttitudeConverter(0, 0, heading) -> Rz(heading), column-major; throttle 0
+      C(0) = ch, C(1) = sh, C(2) = 0.0, C(3) = -sh, C(4) = ch, C(5) = 0.0, C(6) = 0.0, C(7) = 0.0, C(8) = 1.0, C(9) = 0.0;
+      break;
+    case MRSB_TILT_HDG_RATE_CMD:
+      C(0) = 0.0, C(1) = 0.0, C(2) = 1.0, C(3) = 0.0, C(4) = 0.0;
+      break;
+    case MRSB_ACTUATOR_CMD:
+      for (int m = 0; m < MRSB_NM; m++) C(m) = 0.0;
+      break;
+    default:
+      break;
+  }
+}
+
+// Eigen::Quaterniond(Matrix3d) as used by mrs_lib::AttitudeConverter(R); q = x y z w
+DEV void quaternion_of(const double* m /* column-major */, double* q) {
+  auto   M = [&](int r, int c) { return m[3 * c + r]; };
+  double t = M(0, 0) + (M(1, 1) + M(2, 2));
+  if (t > 0.0) {
+    t    = sqrt(t + 1.0);
+    q[3] = 0.5 * t;
+    t    = 0.5 / t;
+    q[0] = (M(2, 1) - M(1, 2)) * t;
+    q[1] = (M(0, 2) - M(2, 0)) * t;
+    q[2] = (M(1, 0) - M(0, 1)) * t;
+  } else {
+    int i = 0;
+    if (M(1, 1) > M(0, 0)) i = 1;
+    if (M(2, 2) > M(i, i)) i = 2;
+    const int j = (i + 1) % 3, k = (j + 1) % 3;
+    t    = sqrt(M(i, i) - M(j, j) - M(k, k) + 1.0);
+    q[i] = 0.5 * t;
+    t    = 0.5 / t;
+    q[3] = (M(k, j) - M(j, k)) * t;
+    q[j] = (M(j, i) + M(i, j)) * t;
+    q[k] = (M(k, i) + M(i, k)) * t;
+  }
+}
+
+// what = 0: publishOdometry (ROSW:340-368) rows [13]; 1: publishIMU (ROSW:374-395) rows [10];
+// 2: publishRangefinder (ROSW:401-420) rows [1]; 3: all of them packed for device-resident callers, rows [17] =
+// odometry 13 | IMU linear acceleration 3 | range 1
+__global__ void observe_kernel(DevState s, int what, int64_t n, const int32_t* __restrict__ idx, double* __restrict__ out, int stride) {
+  const int64_t k = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const int64_t i = at(idx, k);
+  double        x[3], v[3], R[9], w[3], q[4];
+  for (int r = 0; r < 3; r++) {
+    x[r] = s.st[tix(ST_ROWS, r, i)];
+    v[r] = s.st[tix(ST_ROWS, 3 + r, i)];
+    w[r] = s.st[tix(ST_ROWS, 15 + r, i)];
+  }
+  for (int r = 0; r < 9; r++) R[r] = s.st[tix(ST_ROWS, 6 + r, i)];
+  double* o = out + k * stride;
+  if (what == 0 || what == 1 || what == 3) quaternion_of(R, q);
+  double range = 0.0;
+  if (what == 2 || what == 3) {
+    const double bz   = R[8];
+    const double tilt = acos((-R[6]) * 0.0 + ((-R[7]) * 0.0 + (-bz) * -1.0));
+    range             = bz > 0.0 ? (x[2] - s.params[s.pset[s.shard_begin + i]].ground_z) / cos(tilt) + 0.01 : 1.7976931348623157e308;
+    if (range > 40.0) range = 41.0;
+  }
+  if (what == 0 || what == 3) {
+    for (int r = 0; r < 3; r++) o[r] = x[r];
+    for (int r = 0; r < 4; r++) o[3 + r] = q[r];
+    for (int r = 0; r < 3; r++) {
+      o[7 + r]  = R[3 * r] * v[0] + (R[3 * r + 1] * v[1] + R[3 * r + 2] * v[2]);  // R^T v
+      o[10 + r] = w[r];
+    }
+    if (what == 3) {
+      for (int r = 0; r < 3; r++) o[13 + r] = s.imu[tix(F3_ROWS, r, i)];
+      o[16] = range;
+    }
+  } else if (what == 1) {
+    for (int r = 0; r < 3; r++) {
+      o[r]     = w[r];
+      o[3 + r] = s.imu[tix(F3_ROWS, r, i)];
+    }
+    for (int r = 0; r < 4; r++) o[6 + r] = q[r];
+  } else {
+    o[0] = range;
+  }
+}
+
 }  // namespace
+
+int launch_timeout_input(const DevState& s, int64_t n, const int32_t* idx, cudaStream_t st) {
+  if (n <= 0) return 0;
+  timeout_input_kernel<<<nblk(n), 256, 0, st>>>(s, n, idx);
+  return 1;
+}
+int launch_observe(const DevState& s, int what, int64_t n, const int32_t* idx, double* out, int stride, cudaStream_t st) {
+  if (n <= 0) return 0;
+  observe_kernel<<<nblk(n), 256, 0, st>>>(s, what, n, idx, out, stride);
+  return 1;
+}
 
 int launch_scatter_input(const DevState& s, int mode, int64_t n, const int32_t* idx, const double* payload, int stride, cudaStream_t st) {
   if (n <= 0) return 0;

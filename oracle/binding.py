@@ -69,6 +69,9 @@ def lib():
         L.orc_collide_port.restype = C.c_int64
         L.orc_collide_port.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_double, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_int64, C.c_int32]
+        for name in ("orc_get_odometry", "orc_get_imu", "orc_get_rangefinder", "orc_set_mass", "orc_set_ground_z"):
+            getattr(L, name).argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+        L.orc_timeout_input.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
         L.orc_pid_update.restype = C.c_double
         L.orc_pid_update.argtypes = [C.c_void_p] + [C.c_double] * 7
         L.orc_u01.restype = C.c_double
@@ -261,6 +264,35 @@ class OracleSwarm:
         out = np.zeros(24)
         lib().orc_get_pid_state(self.h, uav, _p(out))
         return out
+
+    def timeout_input(self, idx=None):
+        idx = _idx(idx)
+        lib().orc_timeout_input(self.h, self._n(idx), _p(idx))
+
+    def _rows(self, fn, width, idx):
+        idx = _idx(idx)
+        out = np.empty((self._n(idx), width))
+        getattr(lib(), fn)(self.h, len(out), _p(idx), _p(out))
+        return out
+
+    def get_odometry(self, idx=None):
+        return self._rows("orc_get_odometry", 13, idx)
+
+    def get_imu(self, idx=None):
+        return self._rows("orc_get_imu", 10, idx)
+
+    def get_rangefinder(self, idx=None):
+        return self._rows("orc_get_rangefinder", 1, idx)
+
+    def set_mass(self, mass, idx=None):
+        idx = _idx(idx)
+        m = np.ascontiguousarray(np.broadcast_to(mass, (self._n(idx),)), dtype=np.float64)
+        lib().orc_set_mass(self.h, len(m), _p(idx), _p(m))
+
+    def set_ground_z(self, z, idx=None):
+        idx = _idx(idx)
+        z = np.ascontiguousarray(np.broadcast_to(z, (self._n(idx),)), dtype=np.float64)
+        lib().orc_set_ground_z(self.h, len(z), _p(idx), _p(z))
 
     def set_collisions(self, enabled, crash, rebounce):
         self.collisions = (int(enabled), int(crash), float(rebounce))

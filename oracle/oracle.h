@@ -62,6 +62,22 @@ void orc_handle_collisions(orc_swarm* s, int32_t enabled, int32_t crash, double 
 int64_t orc_collide_port(int64_t n, const double* xyz, const double* arm, const double* prop, const double* mass, int32_t crash_mode, double rebounce,
                          double* forces, uint8_t* crashed, int32_t* pairs, int64_t cap, int32_t n_threads);
 
+/* --- the ROS wrapper's arithmetic around the path (src/uav_system_ros.cpp), restated without ROS.
+ * mrs_lib::AttitudeConverter (external dependency ctu-mrs/mrs_lib, not vendored, unpinned) is
+ * restated from its published behaviour: Matrix3d -> Eigen::Quaterniond(R); getHeading() =
+ * atan2 of the xy-projection of the body-x axis; (roll=0, pitch=0, yaw) -> Rz(yaw). */
+/* UavSystemRos::timeoutInput (ROSW:474-647): replace the active command by its "hover" version */
+void orc_timeout_input(orc_swarm* s, int64_t n, const int32_t* idx);
+/* publishOdometry (ROSW:340-368): rows [13] = position xyz, orientation xyzw, body-frame velocity, angular velocity */
+void orc_get_odometry(orc_swarm* s, int64_t n, const int32_t* idx, double* out13);
+/* publishIMU (ROSW:374-395): rows [10] = angular velocity, linear acceleration, orientation xyzw */
+void orc_get_imu(orc_swarm* s, int64_t n, const int32_t* idx, double* out10);
+/* publishRangefinder (ROSW:401-420): rows [1] = range */
+void orc_get_rangefinder(orc_swarm* s, int64_t n, const int32_t* idx, double* out1);
+/* callbackSetMass (ROSW:1028-1054) / callbackSetGroundZ (ROSW:1060-1080) */
+void orc_set_mass(orc_swarm* s, int64_t n, const int32_t* idx, const double* mass);
+void orc_set_ground_z(orc_swarm* s, int64_t n, const int32_t* idx, const double* z);
+
 /* PIDController::update (CTL/pid.hpp:67-96) on caller-held state {last_error, integral}; returns the output */
 double orc_pid_update(double* state2, double kp, double kd, double ki, double saturation, double antiwindup, double error, double dt);
 

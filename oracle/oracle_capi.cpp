@@ -420,6 +420,152 @@ void orc_handle_collisions(orc_swarm* s, int32_t enabled, int32_t crash, double 
   }
 }
 
+// ---- ROS-wrapper arithmetic (src/uav_system_ros.cpp) ------------------------------------------
+static double headingOf(const M3& R) {  // mrs_lib::AttitudeConverter(R).getHeading()
+  return std::atan2(R(1, 0), R(0, 0));
+}
+static void quaternionOf(const M3& m, double* q /* x y z w */) {  // Eigen::Quaterniond(Matrix3d)
+  double t = red3(m(0, 0), m(1, 1), m(2, 2));
+  if (t > 0.0) {
+    t    = std::sqrt(t + 1.0);
+    q[3] = 0.5 * t;
+    t    = 0.5 / t;
+    q[0] = (m(2, 1) - m(1, 2)) * t;
+    q[1] = (m(0, 2) - m(2, 0)) * t;
+    q[2] = (m(1, 0) - m(0, 1)) * t;
+  } else {
+    int i = 0;
+    if (m(1, 1) > m(0, 0)) i = 1;
+    if (m(2, 2) > m(i, i)) i = 2;
+    const int j = (i + 1) % 3, k = (j + 1) % 3;
+    t    = std::sqrt(m(i, i) - m(j, j) - m(k, k) + 1.0);
+    q[i] = 0.5 * t;
+    t    = 0.5 / t;
+    q[3] = (m(k, j) - m(j, k)) * t;
+    q[j] = (m(j, i) + m(i, j)) * t;
+    q[k] = (m(k, i) + m(i, k)) * t;
+  }
+}
+
+void orc_timeout_input(orc_swarm* s, int64_t n, const int32_t* idx) {
+  for (int64_t c = 0; c < n; c++) {
+    UavSystem&   u  = s->uavs[at(idx, c)];
+    const State& st = u.model.state;
+    switch (u.active_input) {  // ROSW:480-646
+      case POSITION_CMD:
+        u.position_cmd.vec = st.x;
+        u.position_cmd.s   = headingOf(st.R);
+        break;
+      case VELOCITY_HDG_CMD:
+        u.velocity_hdg_cmd.vec = v3(0, 0, 0);
+        u.velocity_hdg_cmd.s   = headingOf(st.R);
+        break;
+      case VELOCITY_HDG_RATE_CMD:
+        u.velocity_hdg_rate_cmd.vec = v3(0, 0, 0);
+        u.velocity_hdg_rate_cmd.s   = 0;
+        break;
+      case ACCELERATION_HDG_CMD:
+        u.acceleration_hdg_cmd.vec = v3(0, 0, 0);
+        u.acceleration_hdg_cmd.s   = headingOf(st.R);
+        break;
+      case ACCELERATION_HDG_RATE_CMD:
+        u.acceleration_hdg_rate_cmd.vec = v3(0, 0, 0);
+        u.acceleration_hdg_rate_cmd.s   = 0;
+        break;
+      case ATTITUDE_CMD: {
+        const double h  = headingOf(st.R);
+        const double ch = std::cos(h), sh = std::sin(h);
+        M3           R  = identity3();  // AttitudeConverter(0, 0, heading)
+        R(0, 0) = ch, R(0, 1) = -sh, R(1, 0) = sh, R(1, 1) = ch;
+        u.attitude_cmd.orientation = R;
+        u.attitude_cmd.throttle    = 0.0;
+      } break;
+      case TILT_HDG_RATE_CMD:
+        u.tilt_hdg_rate_cmd              = TiltHdgRate();
+        u.tilt_hdg_rate_cmd.tilt_vector = v3(0, 0, 1);
+        break;
+      case ATTITUDE_RATE_CMD:
+        u.attitude_rate_cmd = AttitudeRate();
+        break;
+      case CONTROL_GROUP_CMD:
+        u.control_group_cmd = ControlGroup();
+        break;
+      case ACTUATOR_CMD:
+        u.actuators_cmd = Actuators();
+        break;
+      case INPUT_UNKNOWN:
+        break;
+    }
+  }
+}
+
+void orc_get_odometry(orc_swarm* s, int64_t n, const int32_t* idx, double* out) {
+  for (int64_t c = 0; c < n; c++) {
+    const State& st = s->uavs[at(idx, c)].model.state;
+    double*      o  = out + 13 * c;
+    for (int k = 0; k < 3; k++) o[k] = st.x[k];
+    quaternionOf(st.R, o + 3);
+    const V3 vb = mul(transpose(st.R), st.v);
+    for (int k = 0; k < 3; k++) {
+      o[7 + k]  = vb[k];
+      o[10 + k] = st.omega[k];
+    }
+  }
+}
+
+void orc_get_imu(orc_swarm* s, int64_t n, const int32_t* idx, double* out) {
+  for (int64_t c = 0; c < n; c++) {
+    const UavSystem& u = s->uavs[at(idx, c)];
+    double*          o = out + 10 * c;
+    for (int k = 0; k < 3; k++) {
+      o[k]     = u.model.state.omega[k];
+      o[3 + k] = u.model.imu_acceleration[k];
+    }
+    quaternionOf(u.model.state.R, o + 6);
+  }
+}
+
+void orc_get_rangefinder(orc_swarm* s, int64_t n, const int32_t* idx, double* out) {
+  for (int64_t c = 0; c < n; c++) {
+    const UavSystem& u      = s->uavs[at(idx, c)];
+    const V3         body_z = u.model.state.R.col(2);
+    const V3         dir    = v3(-body_z[0], -body_z[1], -body_z[2]);
+    const double     tilt   = std::acos(dot(dir, v3(0, 0, -1)));
+    double           range;
+    if (body_z[2] > 0) {
+      range = (u.model.state.x[2] - u.model.params.ground_z) / std::cos(tilt) + 0.01;
+    } else {
+      range = 1.7976931348623157e308;
+    }
+    if (range > 40.0) range = 41.0;
+    out[c] = range;
+  }
+}
+
+void orc_set_mass(orc_swarm* s, int64_t n, const int32_t* idx, const double* mass) {
+  for (int64_t c = 0; c < n; c++) {
+    UavSystem&   u = s->uavs[at(idx, c)];
+    ModelParams  p = u.model.params;
+    const double original = p.mass;
+    p.mass                = mass[c];
+    for (int m = 0; m < p.n_motors; m++) p.allocation_matrix(2, m) = p.mass * (p.allocation_matrix(2, m) / original);
+    p.J       = zero3();
+    p.J(0, 0) = p.mass * (3.0 * p.arm_length * p.arm_length + p.body_height * p.body_height) / 12.0;
+    p.J(1, 1) = p.mass * (3.0 * p.arm_length * p.arm_length + p.body_height * p.body_height) / 12.0;
+    p.J(2, 2) = (p.mass * p.arm_length * p.arm_length) / 2.0;
+    u.setParams(p);
+  }
+}
+
+void orc_set_ground_z(orc_swarm* s, int64_t n, const int32_t* idx, const double* z) {
+  for (int64_t c = 0; c < n; c++) {
+    UavSystem&  u = s->uavs[at(idx, c)];
+    ModelParams p = u.model.params;
+    p.ground_z    = z[c];
+    u.setParams(p);
+  }
+}
+
 double orc_pid_update(double* state2, double kp, double kd, double ki, double saturation, double antiwindup, double error, double dt) {
   Pid p;
   p.setParams(kp, kd, ki, saturation, antiwindup);

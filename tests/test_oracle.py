@@ -244,3 +244,55 @@ def test_squared_distance_is_compared_with_unsquared_lengths():
         xyz = np.array([[0.0, 0.0, 2.0], [d, 0.0, 2.0]])
         pairs, _, _ = O.collide_snapshot(xyz, 0.25, 0.15, 2.0, False, 100.0, engine="port")
         assert (len(pairs) == 2) == hit, d
+
+
+# ---------------------------------------------------------------- ROS-wrapper rows (uav_system_ros.cpp)
+def test_odometry_quaternion_and_body_frame_velocity():
+    s = one(hdg=0.0)
+    yaw = 0.6
+    R = np.array([[np.cos(yaw), -np.sin(yaw), 0], [np.sin(yaw), np.cos(yaw), 0], [0, 0, 1]])
+    s.set_state(R=[R.T.reshape(9)], v=[[1.0, 2.0, 3.0]], omega=[[0.1, 0.2, 0.3]])
+    od = s.get_odometry()[0]
+    assert np.allclose(od[:3], [0, 0, 5])
+    assert np.allclose(od[3:7], [0, 0, np.sin(yaw / 2), np.cos(yaw / 2)], atol=1e-15)  # x y z w
+    assert np.allclose(od[7:10], R.T @ [1.0, 2.0, 3.0], atol=1e-15) and np.allclose(od[10:13], [0.1, 0.2, 0.3])
+    for Rm, q in (([[1, 0, 0], [0, -1, 0], [0, 0, -1]], [1, 0, 0, 0]), ([[-1, 0, 0], [0, 1, 0], [0, 0, -1]], [0, 1, 0, 0]),
+                  ([[-1, 0, 0], [0, -1, 0], [0, 0, 1]], [0, 0, 1, 0])):  # the three trace <= 0 branches
+        s.set_state(R=[np.array(Rm, dtype=float).T.reshape(9)])
+        assert np.allclose(s.get_odometry()[0, 3:7], q, atol=1e-15)
+
+
+def test_rangefinder_model():
+    s = one(pos=(0, 0, 5), ground_enabled=True, ground_z=1.0)
+    assert np.isclose(s.get_rangefinder()[0, 0], 4.0 + 0.01, atol=1e-12)
+    th = 0.4
+    R = np.array([[1, 0, 0], [0, np.cos(th), -np.sin(th)], [0, np.sin(th), np.cos(th)]])
+    s.set_state(R=[R.T.reshape(9)])
+    assert np.isclose(s.get_rangefinder()[0, 0], 4.0 / np.cos(th) + 0.01, atol=1e-12)
+    s.set_state(x=[[0, 0, 60.0]])
+    assert s.get_rangefinder()[0, 0] == 41.0  # beyond 40 m
+    s.set_state(x=[[0, 0, 5.0]], R=[np.diag([1.0, -1.0, -1.0]).reshape(9)])
+    assert s.get_rangefinder()[0, 0] == 41.0  # inverted
+
+
+def test_timeout_input_holds_position_and_heading():
+    s = one(hdg=0.0)
+    s.set_input(O.POSITION_CMD, [[30.0, 0.0, 5.0, 0.0]])
+    s.make_step(0.01, 150)
+    x0 = s.get_state()["x"][0].copy()
+    assert x0[0] > 2.0
+    s.timeout_input()
+    s.make_step(0.01, 1500)
+    st = s.get_state()
+    assert np.max(np.abs(st["x"][0] - x0)) < 0.05 and np.max(np.abs(st["v"])) < 1e-3  # settles where the command timed out
+
+
+def test_set_mass_rescales_row_two_and_inertia():
+    s = one("f550")
+    p0 = s.get_params(0)
+    s.set_mass(3.0)
+    p1 = s.get_params(0)
+    assert p1.mass == 3.0
+    assert np.allclose(np.array(p1.allocation_matrix[16:22]), np.array(p0.allocation_matrix[16:22]) * 3.0 / 2.3, rtol=1e-15)
+    assert list(p1.allocation_matrix[:16]) == list(p0.allocation_matrix[:16]) and list(p1.allocation_matrix[24:]) == list(p0.allocation_matrix[24:])
+    assert np.isclose(p1.J[8], 3.0 * 0.27 * 0.27 / 2.0) and np.isclose(p1.J[0], 3.0 * (3 * 0.27 ** 2 + 0.1 ** 2) / 12.0)
