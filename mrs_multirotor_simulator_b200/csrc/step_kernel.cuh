@@ -23,7 +23,9 @@
 //     multiplication by such a reciprocal (<= 2 ulp instead of correctly rounded);
 //   * the NaN -> 0 scrub of the slopes (MM:361-365) and the NaN -> restore check (MM:228-233) first
 //     screen the exponent fields with integer max (any Inf/NaN?) and only then do the exact test;
-//   * FMA contraction is on.
+//   * every fused multiply-add is written out (`fma`) and the file is compiled with -fmad=false, so
+//     that all instantiations of the kernel (direct / staged, K = 1 / K > 1, any register budget)
+//     produce the same bits: K fused substeps equal K launches, a sharded swarm equals the unsharded one.
 // All of these change results only at rounding level (<= a few ulp per operation); parity with the
 // CPU oracle is asserted within the tolerances of DESIGN.md §5 by tests/test_step_parity.py.
 //
@@ -77,8 +79,8 @@ DEV Vec3 mk(double x, double y, double z) {
 DEV Vec3   operator+(Vec3 a, Vec3 b) { return mk(a.x + b.x, a.y + b.y, a.z + b.z); }
 DEV Vec3   operator-(Vec3 a, Vec3 b) { return mk(a.x - b.x, a.y - b.y, a.z - b.z); }
 DEV Vec3   operator*(Vec3 a, double s) { return mk(a.x * s, a.y * s, a.z * s); }
-DEV double dot(Vec3 a, Vec3 b) { return a.x * b.x + (a.y * b.y + a.z * b.z); }
-DEV Vec3   cross(Vec3 a, Vec3 b) { return mk(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+DEV double dot(Vec3 a, Vec3 b) { return fma(a.x, b.x, fma(a.y, b.y, a.z * b.z)); }
+DEV Vec3   cross(Vec3 a, Vec3 b) { return mk(fma(a.y, b.z, -(a.z * b.y)), fma(a.z, b.x, -(a.x * b.z)), fma(a.x, b.y, -(a.y * b.x))); }
 DEV Vec3   fma3(Vec3 a, double s, Vec3 b) { return mk(fma(a.x, s, b.x), fma(a.y, s, b.y), fma(a.z, s, b.z)); }  // a*s + b
 // Eigen normalized(): divide by the norm only if the squared norm is positive
 DEV Vec3 normalized(Vec3 a) {
@@ -109,11 +111,11 @@ DEV Rot reortho(const Rot& R) {
 #if !MRSB_CHOL_PARALLEL
   const double i00 = rsqrt_fast(g00);
   const double l10 = g10 * i00, l20 = g20 * i00;
-  const double d1  = g11 - l10 * l10;
+  const double d1  = fma(-l10, l10, g11);
   const double i11 = rsqrt_fast(d1);
   const double l11 = d1 * i11;
-  const double l21 = (g21 - l20 * l10) * i11;
-  const double d2  = g22 - (l20 * l20 + l21 * l21);
+  const double l21 = fma(-l20, l10, g21) * i11;
+  const double d2  = fma(-l21, l21, fma(-l20, l20, g22));
   const double i22 = rsqrt_fast(d2);
 #else
   const double m1  = fma(g00, g11, -(g10 * g10));
@@ -130,11 +132,11 @@ DEV Rot reortho(const Rot& R) {
   const double l11 = s1 * i00;   // L11
   const double i22 = s1 * rd;    // 1 / L22
   const double l10 = g10 * i00, l20 = g20 * i00;
-  const double l21 = (g21 - l20 * l10) * i11;
+  const double l21 = fma(-l20, l10, g21) * i11;
 #endif
   const double a10 = -(l10 * i00) * i11;
   const double a21 = -(l21 * i11) * i22;
-  const double a20 = (l10 * l21 - l20 * l11) * (i00 * i11 * i22);
+  const double a20 = fma(l10, l21, -(l20 * l11)) * ((i00 * i11) * i22);
   Rot          N;
   N.c0 = fma3(R.c2, a20, fma3(R.c1, a10, R.c0 * i00));
   N.c1 = fma3(R.c2, a21, R.c1 * i11);
@@ -167,12 +169,12 @@ DEV Slope derivative(Vec3 v, const Rot& Rraw, Vec3 w, const Frozen& f, const Dev
   const double sp    = vv * rsqrt_fast(vv);
   const double speed = vv > 1e-290 ? sp : 0.0;  // |v| < 1e-145 m/s: the drag term is zero to 1e-290
   const double kd    = f.air_m * speed;
-  k.dv = mk(fma(R.c2.x, f.thrust_m, f.f_m.x) - kd * v.x, fma(R.c2.y, f.thrust_m, f.f_m.y) - kd * v.y,
-            (fma(R.c2.z, f.thrust_m, f.f_m.z) - f.g) - kd * v.z);
+  k.dv = mk(fma(-kd, v.x, fma(R.c2.x, f.thrust_m, f.f_m.x)), fma(-kd, v.y, fma(R.c2.y, f.thrust_m, f.f_m.y)),
+            fma(-kd, v.z, fma(R.c2.z, f.thrust_m, f.f_m.z) - f.g));
   // R * [w]x
-  k.dR.c0 = R.c1 * w.z - R.c2 * w.y;
-  k.dR.c1 = R.c2 * w.x - R.c0 * w.z;
-  k.dR.c2 = R.c0 * w.y - R.c1 * w.x;
+  k.dR.c0 = fma3(R.c1, w.z, R.c2 * -w.y);
+  k.dR.c1 = fma3(R.c2, w.x, R.c0 * -w.z);
+  k.dR.c2 = fma3(R.c0, w.y, R.c1 * -w.x);
   if (jdiag) {
     const Vec3 Jw = mk(Jd.x * w.x, Jd.y * w.y, Jd.z * w.z);
     const Vec3 r  = f.tau - cross(w, Jw);
@@ -180,9 +182,9 @@ DEV Slope derivative(Vec3 v, const Rot& Rraw, Vec3 w, const Frozen& f, const Dev
   } else {
     const double* J  = P->J;
     const double* Ji = P->Jinv;
-    const Vec3    Jw = mk(J[0] * w.x + (J[1] * w.y + J[2] * w.z), J[3] * w.x + (J[4] * w.y + J[5] * w.z), J[6] * w.x + (J[7] * w.y + J[8] * w.z));
+    const Vec3    Jw = mk(dot(mk(J[0], J[1], J[2]), w), dot(mk(J[3], J[4], J[5]), w), dot(mk(J[6], J[7], J[8]), w));
     const Vec3    r  = f.tau - cross(w, Jw);
-    k.dw = mk(Ji[0] * r.x + (Ji[1] * r.y + Ji[2] * r.z), Ji[3] * r.x + (Ji[4] * r.y + Ji[5] * r.z), Ji[6] * r.x + (Ji[7] * r.y + Ji[8] * r.z));
+    k.dw = mk(dot(mk(Ji[0], Ji[1], Ji[2]), r), dot(mk(Ji[3], Ji[4], Ji[5]), r), dot(mk(Ji[6], Ji[7], Ji[8]), r));
   }
   if (EXACT) {
     k.dv    = nan0(k.dv);
@@ -260,7 +262,7 @@ DEV unsigned rk4(const Rigid& a, Rigid& out, double dt, const Frozen& fz, const 
 DEV double pid(double e, double dt, double inv_dt, double kp, double kd, double ki, double sat, double aw, double& last, double& integ) {
   const double diff = (e - last) * inv_dt;
   last              = e;
-  double u          = kp * e + kd * diff + ki * integ;
+  double u          = fma(ki, integ, fma(kd, diff, kp * e));
   if (sat > 0.0) {
     if (u >= sat) {
       u = sat;
@@ -268,7 +270,7 @@ DEV double pid(double e, double dt, double inv_dt, double kp, double kd, double 
       u = -sat;
     }
   }
-  if (aw > 0.0 && fabs(u) < aw) integ += e * dt;
+  if (aw > 0.0 && fabs(u) < aw) integ = fma(e, dt, integ);
   return u;
 }
 
@@ -285,8 +287,12 @@ DEV Vec3 attitude_error(const Rot& Rd, const Rot& R) {
 #ifndef MRSB_STEP_THREADS
 #define MRSB_STEP_THREADS 128
 #endif
+// CTAs per SM the register allocator aims for.  Measured on B200 (profiles/r1_history.md): the K = 1
+// kernels gain from 3 CTAs (168 registers, 12 warps per SM) except PositionCmd, whose extra PID
+// state then spills; the K > 1 kernels keep PID state, command and motor speeds live across the
+// substep loop and are faster with 2 CTAs (<= 255 registers, no spills).
 #ifndef MRSB_STEP_MINB
-#define MRSB_STEP_MINB 2
+#define MRSB_STEP_MINB(ONE, MODE_T) (((ONE) && (MODE_T) != MRSB_POSITION_CMD) ? 3 : 2)
 #endif
 
 // ---- TMA / mbarrier plumbing for the staged kernel ---------------------------------------------
@@ -510,7 +516,7 @@ DEV void step_uav(const DevState& s, const TileIn& in, const int64_t tile, const
         throttle          = (sqrt_fast(tf * P->inv_kf_n) - min_rpm) * P->inv_rpm_range;
         if (mode == MRSB_ACCELERATION_HDG_CMD) {
           const double ch = c[CMD_COS], sh = c[CMD_SIN];
-          const double num = n.x * ch + n.y * sh;
+          const double num = fma(n.x, ch, n.y * sh);
           const double z3  = (num == 0.0) ? 0.0 : -num * rcp_fast(n.z);
           Rd.c2            = n;
           Rd.c0            = normalized(mk(ch, sh, z3));
@@ -544,14 +550,14 @@ DEV void step_uav(const DevState& s, const TileIn& in, const int64_t tile, const
         double rz = pid(e.z, dt, inv_dt, P->att_kp, P->att_kd, P->att_ki, P->att_sat_yaw, 0.1, pd[16], pd[17]);
         if (tilt) {
           // intrinsicBodyRateToHeadingRate (:177-206): d/dt atan2(R10, R00) under body rates (rx,ry,rz)
-          const double rd00 = R.c1.x * rz - R.c2.x * ry;  // (R*[w]x)(0,0)
-          const double rd10 = R.c1.y * rz - R.c2.y * ry;  // (R*[w]x)(1,0)
+          const double rd00 = fma(R.c1.x, rz, -(R.c2.x * ry));  // (R*[w]x)(0,0)
+          const double rd10 = fma(R.c1.y, rz, -(R.c2.y * ry));  // (R*[w]x)(1,0)
           const double hx = R.c0.x, hy = R.c0.y;
-          const double den = hx * hx + hy * hy;
+          const double den = fma(hx, hx, hy * hy);
           double       parasitic = 0.0;
           if (!(fabs(den) <= 1e-5)) {
             const double iden = rcp_fast(den);
-            parasitic         = (-hy * iden) * rd00 + (hx * iden) * rd10;
+            parasitic         = fma(-hy * iden, rd00, (hx * iden) * rd10);
           }
           // getYawRateIntrinsic (:212-251)
           const double hr  = sc - parasitic;
@@ -559,7 +565,7 @@ DEV void step_uav(const DevState& s, const TileIn& in, const int64_t tile, const
           if (!(fabs(hr) < 1e-3)) {
             const Vec3   orb  = mk(-hr * hy, hr * hx, 0.0);
             const Vec3   b    = normalized(mk(-hy, hx, 0.0));
-            const double bp   = b.x * R.c1.x + (b.y * R.c1.y + b.z * R.c1.z);
+            const double bp   = dot(b, R.c1);
             const Vec3   proj = b * bp;
             const double on = sqrt_fast(dot(orb, orb)), pn = sqrt_fast(dot(proj, proj));
             if (!(fabs(pn) < 1e-5)) {
@@ -584,7 +590,7 @@ DEV void step_uav(const DevState& s, const TileIn& in, const int64_t tile, const
 #pragma unroll
         for (int m = 0; m < MRSB_NM; m++) {
           if (m < nm) {
-            u[m] = (P->mix[m][0] * vec.x + P->mix[m][1] * vec.y) + (P->mix[m][2] * vec.z + P->mix[m][3] * throttle);
+            u[m] = fma(P->mix[m][0], vec.x, P->mix[m][1] * vec.y) + fma(P->mix[m][2], vec.z, P->mix[m][3] * throttle);
             mn   = fmin(mn, u[m]);
           }
         }
@@ -608,7 +614,7 @@ DEV void step_uav(const DevState& s, const TileIn& in, const int64_t tile, const
               const double r0 = vec.x * isc, r1 = vec.y * isc, r2 = vec.z * isc;
 #pragma unroll
               for (int m = 0; m < MRSB_NM; m++)
-                if (m < nm) u[m] = (P->mix[m][0] * r0 + P->mix[m][1] * r1) + (P->mix[m][2] * r2 + P->mix[m][3] * throttle);
+                if (m < nm) u[m] = fma(P->mix[m][0], r0, P->mix[m][1] * r1) + fma(P->mix[m][2], r2, P->mix[m][3] * throttle);
             } else {
               const double imx = rcp_fast(mx);
 #pragma unroll
@@ -664,7 +670,7 @@ DEV void step_uav(const DevState& s, const TileIn& in, const int64_t tile, const
           t1 = fma(P->alloc[1][m], sq, t1);
           t2 = fma(P->alloc[2][m], sq, t2);
           t3 = fma(P->alloc[3][m], sq, t3);
-          rpm[m] = filt * rpm[m] + (1.0 - filt) * target;
+          rpm[m] = fma(filt, rpm[m], (1.0 - filt) * target);
           if (last) ST(o_rpm, m, rpm[m]);
         }
       }
@@ -716,7 +722,7 @@ DEV void step_uav(const DevState& s, const TileIn& in, const int64_t tile, const
     }
 
     // MM:280-281 fabricated accelerometer
-    const Vec3 lin = mk((v.x - vprev.x) * inv_dt, (v.y - vprev.y) * inv_dt, (v.z - vprev.z) * inv_dt + g);
+    const Vec3 lin = mk((v.x - vprev.x) * inv_dt, (v.y - vprev.y) * inv_dt, fma(v.z - vprev.z, inv_dt, g));
     imu            = mk(dot(R.c0, lin), dot(R.c1, lin), dot(R.c2, lin));
     vprev          = v;
   }
@@ -777,7 +783,7 @@ DEV void step_uav(const DevState& s, const TileIn& in, const int64_t tile, const
 
 // ---- direct kernel: one CTA per tile, inputs read straight from HBM ----------------------------
 template <int NM_T, int MODE_T, bool ONE>
-__global__ void __launch_bounds__(MRSB_STEP_THREADS, MRSB_STEP_MINB) uav_step_kernel(DevState s, double dt, int k_sub, int any_moment) {
+__global__ void __launch_bounds__(MRSB_STEP_THREADS, MRSB_STEP_MINB(ONE, MODE_T)) uav_step_kernel(DevState s, double dt, int k_sub, int any_moment) {
   const int64_t tile = blockIdx.x;
   TileIn        in;
   in.st   = s.st + (tile * ST_ROWS) * MRSB_TILE + threadIdx.x;
@@ -820,7 +826,7 @@ DEV void stage_tile(const DevState& s, double* sm, uint64_t* bar, int64_t tile) 
 // BULK: the shard has peers — the tile's packed positions leave through shared memory as TMA bulk
 // stores to the local gather buffer and to every peer's (fused all-gather over NVLink).
 template <int NM_T, int MODE_T, bool ONE, bool BULK>
-__global__ void __launch_bounds__(MRSB_STEP_THREADS, MRSB_STEP_MINB)
+__global__ void __launch_bounds__(MRSB_STEP_THREADS, MRSB_STEP_MINB(ONE, MODE_T))
     uav_step_staged_kernel(DevState s, const __grid_constant__ DevParams params, double dt, int k_sub, int any_moment, int64_t n_tiles) {
   // `params`: the one parameter set of the whole batch, passed BY VALUE: it lives in the constant
   // bank, so airframe constants and gains are instruction operands instead of ~80 loads per UAV
