@@ -342,6 +342,13 @@ def run_b200(args):
                          "peak_tflops_measured_dfma": fp64.value, "flop_per_uav_step_as_written": STEP_FLOP_PER_UAV},
                 "copy_gbs_measured_here": copy.value,
                 "collision_pass": {"ms": coll_ms, "share_of_tick": coll_ms / (coll_ms + step_ms), "n_hashed": N_UAVS}}
+    fp64_file = os.path.join(ROOT, "profiles", "step_kernel_fp64.json")
+    if os.path.exists(fp64_file):  # executed FP64 work of the same kernel (ncu), reported beside the as-written census
+        with open(fp64_file) as f:
+            ex = json.load(f)["executed_fp64_flop_per_uav_step"]
+        tf = n_local * ex / (step_ms * 1e-3) / 1e12
+        roofline["fp64"].update({"executed_flop_per_uav_step": ex, "achieved_tflops_executed": tf,
+                                 "frac_of_measured_dfma_peak": min(tf, roofline["fp64"]["achieved_tflops_as_written_census"]) / fp64.value})
     traffic_file = os.path.join(ROOT, "profiles", "step_kernel_traffic.json")
     if os.path.exists(traffic_file):
         with open(traffic_file) as f:

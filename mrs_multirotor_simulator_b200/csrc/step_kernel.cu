@@ -67,7 +67,7 @@ int launch_p2p_wait(const unsigned long long* flags, int n_ranks, int rank, unsi
   static long long budget = 0;
   if (!budget) {
     const char* e = getenv("MRSB_P2P_TIMEOUT_MS");
-    budget        = (e ? atoll(e) : 3000LL) * 2000000LL;  // ~2 GHz SM clock
+    budget        = (e ? atoll(e) : 20000LL) * 2000000LL;  // default 20 s at ~2 GHz SM clock
   }
   p2p_wait_kernel<<<1, 32, 0, stream>>>(flags, n_ranks, rank, epoch, status, budget);
   return 1;

@@ -112,3 +112,55 @@ def test_set_mass_and_set_ground_z_services():
     assert_parity(orc, gpu, what="landed")
     z = gpu.get_state()["x"][:, 2]
     assert np.all(z[low] == 2.0) and np.all(z[heavy] == 0.0)
+
+
+def test_device_resident_commands_and_state_view():
+    """mrsb_set_input_device (commands produced on the GPU) and mrsb_get_device_view (tiled state arrays)."""
+    import torch
+
+    from mrs_multirotor_simulator_b200 import UavBatch
+
+    n = 1000  # not a multiple of the 128-UAV tile
+    spawn = grid_spawn(n, z=8.0)
+    cmd = np.stack([rand(3, 1, n, -2, 2), rand(3, 2, n, -2, 2), rand(3, 3, n, -1, 1), rand(3, 4, n, -3, 3)], axis=1)
+    a = UavBatch([af("x500")], spawn_xyz=spawn, n=n)
+    b = UavBatch([af("x500")], spawn_xyz=spawn, n=n)
+    a.set_input(O.VELOCITY_HDG_CMD, cmd)
+    stream = torch.cuda.ExternalStream(b.stream)
+    with torch.cuda.stream(stream):
+        dev_cmd = torch.from_numpy(cmd).cuda()
+    stream.synchronize()
+    b.set_input_device(O.VELOCITY_HDG_CMD, dev_cmd.data_ptr(), 4)
+    # a subset, addressed by a device index list, gets a different command on both
+    sub = np.arange(5, n, 7).astype(np.int32)
+    sub_cmd = np.tile([0.0, 0.0, 1.0, 0.5], (len(sub), 1))
+    a.set_input(O.VELOCITY_HDG_RATE_CMD, sub_cmd, idx=sub)
+    with torch.cuda.stream(stream):
+        d_idx, d_sub = torch.from_numpy(sub).cuda(), torch.from_numpy(sub_cmd).cuda()
+    stream.synchronize()
+    b.set_input_device(O.VELOCITY_HDG_RATE_CMD, d_sub.data_ptr(), 4, n=len(sub), idx_ptr=d_idx.data_ptr())
+    for s in (a, b):
+        for _ in range(20):
+            s.make_step(0.01, 5)
+    sa, sb = a.get_full_state(), b.get_full_state()
+    for k in sa:
+        assert np.array_equal(sa[k], sb[k]), k
+    assert np.array_equal(a.get_input_mode(), b.get_input_mode()) and set(np.unique(b.get_input_mode())) == {8, 9}
+
+    # tiled device view: component c of UAV i at ptr[((i // tile) * rows + c) * tile + i % tile]
+    from cuda.bindings import runtime as cudart
+
+    v = b.device_view()
+    assert v.tile == 128 and v.state_rows == 18
+    n_tiles = (n + v.tile - 1) // v.tile
+    raw = np.zeros(n_tiles * v.state_rows * v.tile)
+    b.sync()
+    (err,) = cudart.cudaMemcpy(raw.ctypes.data, v.state, raw.nbytes, cudart.cudaMemcpyKind.cudaMemcpyDeviceToHost)
+    assert int(err) == 0
+    tiles = raw.reshape(n_tiles, v.state_rows, v.tile)
+    i = np.arange(n)
+    for c in range(3):
+        assert np.array_equal(tiles[i // v.tile, c, i % v.tile], sb["x"][:, c])
+        assert np.array_equal(tiles[i // v.tile, 15 + c, i % v.tile], sb["omega"][:, c])
+    for c in range(9):
+        assert np.array_equal(tiles[i // v.tile, 6 + c, i % v.tile], sb["R"][:, c])
