@@ -40,6 +40,51 @@ def build(fast=False):
     subprocess.run(["make", "-s", "-C", HERE] + targets, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
 
 
+def _bind_stepping(L):
+    L.orc_create.restype = C.c_void_p
+    L.orc_create.argtypes = [C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.orc_destroy.argtypes = [C.c_void_p]
+    L.orc_set_input.argtypes = [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32]
+    L.orc_set_feedforward.argtypes = [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]
+    L.orc_make_step.argtypes = [C.c_void_p, C.c_double, C.c_int32, C.c_int32]
+    L.orc_get_state.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 8
+    L.orc_set_state.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 6
+    L.orc_crash.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
+    L.orc_has_crashed.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+    L.orc_apply_force.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+    L.orc_get_force.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+    L.orc_set_external_moment.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+    L.orc_set_params.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+    L.orc_get_params.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
+    L.orc_set_controller_params.argtypes = [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]
+    L.orc_get_mixer_allocation.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
+    L.orc_get_pid_state.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
+    L.orc_pid_update.restype = C.c_double
+    L.orc_pid_update.argtypes = [C.c_void_p] + [C.c_double] * 7
+    L.orc_model_params_default.argtypes = [C.c_void_p]
+
+
+_refsys = {}
+
+
+def refsys_lib(flavour="default"):
+    """The reference's own UavSystem compiled against oracle/shim (oracle/_ref); None if never built.
+    flavour "default": the stand-in follows the same Eigen evaluation rules as uav_oracle.hpp;
+    flavour "vec": the alternative reading (packet-ordered contiguous reductions, coefficient-based
+    matrix x fixed-vector products) — used to measure how much an Eigen evaluation-order choice can matter."""
+    if flavour not in _refsys:
+        name = {"default": "libref_uavsystem.so", "vec": "libref_uavsystem_vec.so"}[flavour]
+        path = os.path.join(HERE, "_ref", name)
+        if not os.path.exists(path):
+            return None
+        L = C.CDLL(path)
+        L.ref_uavsystem_flavour.restype = C.c_int32
+        assert L.ref_uavsystem_flavour() == {"default": 1, "vec": 2}[flavour]
+        _bind_stepping(L)
+        _refsys[flavour] = L
+    return _refsys[flavour]
+
+
 def lib():
     global _lib
     if _lib is None:
@@ -47,24 +92,7 @@ def lib():
         if not os.path.exists(path):
             build()
         L = C.CDLL(path)
-        L.orc_create.restype = C.c_void_p
-        L.orc_create.argtypes = [C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
-        L.orc_destroy.argtypes = [C.c_void_p]
-        L.orc_set_input.argtypes = [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32]
-        L.orc_set_feedforward.argtypes = [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]
-        L.orc_make_step.argtypes = [C.c_void_p, C.c_double, C.c_int32, C.c_int32]
-        L.orc_get_state.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 8
-        L.orc_set_state.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 6
-        L.orc_crash.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
-        L.orc_has_crashed.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
-        L.orc_apply_force.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
-        L.orc_get_force.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
-        L.orc_set_external_moment.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
-        L.orc_set_params.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
-        L.orc_get_params.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
-        L.orc_set_controller_params.argtypes = [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]
-        L.orc_get_mixer_allocation.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
-        L.orc_get_pid_state.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
+        _bind_stepping(L)
         L.orc_handle_collisions.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_double, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]
         L.orc_collide_port.restype = C.c_int64
         L.orc_collide_port.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_double, C.c_void_p, C.c_void_p,
@@ -72,11 +100,8 @@ def lib():
         for name in ("orc_get_odometry", "orc_get_imu", "orc_get_rangefinder", "orc_set_mass", "orc_set_ground_z"):
             getattr(L, name).argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
         L.orc_timeout_input.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
-        L.orc_pid_update.restype = C.c_double
-        L.orc_pid_update.argtypes = [C.c_void_p] + [C.c_double] * 7
         L.orc_u01.restype = C.c_double
         L.orc_u01.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64]
-        L.orc_model_params_default.argtypes = [C.c_void_p]
         _lib = L
     return _lib
 
@@ -156,8 +181,11 @@ def u01(seed, stream, index):
 class OracleSwarm:
     """N independent restated UavSystems + the reference node's collision loop."""
 
+    def _library(self):
+        return lib()
+
     def __init__(self, types, type_of_uav=None, spawn_xyz=None, spawn_heading=None, n=None):
-        L = lib()
+        L = self._L = self._library()
         self.types = [t if isinstance(t, OrcModelParams) else params_from_dict(t) for t in types]
         arr = (OrcModelParams * len(self.types))(*self.types)
         if n is None:
@@ -171,7 +199,7 @@ class OracleSwarm:
 
     def __del__(self):
         if getattr(self, "h", None):
-            lib().orc_destroy(self.h)
+            self._L.orc_destroy(self.h)
             self.h = None
 
     def _n(self, idx):
@@ -181,98 +209,98 @@ class OracleSwarm:
         idx = _idx(idx)
         n = self._n(idx)
         if mode == INPUT_UNKNOWN:
-            lib().orc_set_input(self.h, mode, n, _p(idx), None, 0)
+            self._L.orc_set_input(self.h, mode, n, _p(idx), None, 0)
             return
         pl = np.ascontiguousarray(payload, dtype=np.float64).reshape(n, -1)
         if mode == ACTUATOR_CMD and pl.shape[1] < 8:
             pl = np.ascontiguousarray(np.pad(pl, ((0, 0), (0, 8 - pl.shape[1]))))
         assert pl.shape[1] == STRIDE[mode], (mode, pl.shape)
-        lib().orc_set_input(self.h, mode, n, _p(idx), _p(pl), pl.shape[1])
+        self._L.orc_set_input(self.h, mode, n, _p(idx), _p(pl), pl.shape[1])
 
     def set_feedforward(self, kind, payload, idx=None):
         idx = _idx(idx)
         n = self._n(idx)
         pl = np.ascontiguousarray(payload, dtype=np.float64).reshape(n, 4)
-        lib().orc_set_feedforward(self.h, kind, n, _p(idx), _p(pl))
+        self._L.orc_set_feedforward(self.h, kind, n, _p(idx), _p(pl))
 
     def make_step(self, dt, n_steps=1, n_threads=1):
-        lib().orc_make_step(self.h, dt, n_steps, n_threads)
+        self._L.orc_make_step(self.h, dt, n_steps, n_threads)
 
     def get_state(self, idx=None):
         idx = _idx(idx)
         n = self._n(idx)
         out = {"x": np.empty((n, 3)), "v": np.empty((n, 3)), "R": np.empty((n, 9)), "omega": np.empty((n, 3)), "motor_rpm": np.empty((n, 8)),
                "v_prev": np.empty((n, 3)), "imu": np.empty((n, 3))}
-        lib().orc_get_state(self.h, n, _p(idx), *[_p(out[k]) for k in ("x", "v", "R", "omega", "motor_rpm", "v_prev", "imu")])
+        self._L.orc_get_state(self.h, n, _p(idx), *[_p(out[k]) for k in ("x", "v", "R", "omega", "motor_rpm", "v_prev", "imu")])
         return out
 
     def set_state(self, idx=None, x=None, v=None, R=None, omega=None, motor_rpm=None):
         idx = _idx(idx)
         n = self._n(idx)
         arrs = [None if a is None else np.ascontiguousarray(a, dtype=np.float64).reshape(n, -1) for a in (x, v, R, omega, motor_rpm)]
-        lib().orc_set_state(self.h, n, _p(idx), *[_p(a) for a in arrs])
+        self._L.orc_set_state(self.h, n, _p(idx), *[_p(a) for a in arrs])
 
     def crash(self, idx=None):
         idx = _idx(idx)
-        lib().orc_crash(self.h, self._n(idx), _p(idx))
+        self._L.orc_crash(self.h, self._n(idx), _p(idx))
 
     def has_crashed(self, idx=None):
         idx = _idx(idx)
         out = np.zeros(self._n(idx), dtype=np.int32)
-        lib().orc_has_crashed(self.h, len(out), _p(idx), _p(out))
+        self._L.orc_has_crashed(self.h, len(out), _p(idx), _p(out))
         return out
 
     def apply_force(self, f, idx=None):
         idx = _idx(idx)
         n = self._n(idx)
         f = np.ascontiguousarray(f, dtype=np.float64).reshape(n, 3)
-        lib().orc_apply_force(self.h, n, _p(idx), _p(f))
+        self._L.orc_apply_force(self.h, n, _p(idx), _p(f))
 
     def get_force(self, idx=None):
         idx = _idx(idx)
         out = np.empty((self._n(idx), 3))
-        lib().orc_get_force(self.h, len(out), _p(idx), _p(out))
+        self._L.orc_get_force(self.h, len(out), _p(idx), _p(out))
         return out
 
     def set_external_moment(self, m, idx=None):
         idx = _idx(idx)
         n = self._n(idx)
         m = np.ascontiguousarray(m, dtype=np.float64).reshape(n, 3)
-        lib().orc_set_external_moment(self.h, n, _p(idx), _p(m))
+        self._L.orc_set_external_moment(self.h, n, _p(idx), _p(m))
 
     def set_params(self, params, idx=None):
         idx = _idx(idx)
         p = params if isinstance(params, OrcModelParams) else params_from_dict(params)
-        lib().orc_set_params(self.h, self._n(idx), _p(idx), C.byref(p))
+        self._L.orc_set_params(self.h, self._n(idx), _p(idx), C.byref(p))
 
     def get_params(self, uav):
         p = OrcModelParams()
-        lib().orc_get_params(self.h, uav, C.byref(p))
+        self._L.orc_get_params(self.h, uav, C.byref(p))
         return p
 
     def set_controller_params(self, which, values, idx=None):
         idx = _idx(idx)
         v = np.ascontiguousarray(values, dtype=np.float64)
-        lib().orc_set_controller_params(self.h, {"mixer": 0, "rate": 1, "attitude": 2, "velocity": 3, "position": 4}[which], self._n(idx), _p(idx), _p(v))
+        self._L.orc_set_controller_params(self.h, {"mixer": 0, "rate": 1, "attitude": 2, "velocity": 3, "position": 4}[which], self._n(idx), _p(idx), _p(v))
 
     def get_mixer_allocation(self, uav=0):
         out = np.zeros((8, 4))
-        lib().orc_get_mixer_allocation(self.h, uav, _p(out))
+        self._L.orc_get_mixer_allocation(self.h, uav, _p(out))
         return out
 
     def get_pid_state(self, uav=0):
         out = np.zeros(24)
-        lib().orc_get_pid_state(self.h, uav, _p(out))
+        self._L.orc_get_pid_state(self.h, uav, _p(out))
         return out
 
     def timeout_input(self, idx=None):
         idx = _idx(idx)
-        lib().orc_timeout_input(self.h, self._n(idx), _p(idx))
+        self._L.orc_timeout_input(self.h, self._n(idx), _p(idx))
 
     def _rows(self, fn, width, idx):
         idx = _idx(idx)
         out = np.empty((self._n(idx), width))
-        getattr(lib(), fn)(self.h, len(out), _p(idx), _p(out))
+        getattr(self._L, fn)(self.h, len(out), _p(idx), _p(out))
         return out
 
     def get_odometry(self, idx=None):
@@ -287,12 +315,12 @@ class OracleSwarm:
     def set_mass(self, mass, idx=None):
         idx = _idx(idx)
         m = np.ascontiguousarray(np.broadcast_to(mass, (self._n(idx),)), dtype=np.float64)
-        lib().orc_set_mass(self.h, len(m), _p(idx), _p(m))
+        self._L.orc_set_mass(self.h, len(m), _p(idx), _p(m))
 
     def set_ground_z(self, z, idx=None):
         idx = _idx(idx)
         z = np.ascontiguousarray(np.broadcast_to(z, (self._n(idx),)), dtype=np.float64)
-        lib().orc_set_ground_z(self.h, len(z), _p(idx), _p(z))
+        self._L.orc_set_ground_z(self.h, len(z), _p(idx), _p(z))
 
     def set_collisions(self, enabled, crash, rebounce):
         self.collisions = (int(enabled), int(crash), float(rebounce))
@@ -308,8 +336,27 @@ class OracleSwarm:
         pairs = np.zeros((cap, 2), dtype=np.int32)
         cnt = C.c_int64(0)
         en, cr, rb = self.collisions
-        lib().orc_handle_collisions(self.h, en, cr, rb, fn, n_threads, _p(pairs), cap, C.byref(cnt))
+        self._L.orc_handle_collisions(self.h, en, cr, rb, fn, n_threads, _p(pairs), cap, C.byref(cnt))
         return pairs[:min(cnt.value, cap)].copy()
+
+
+class RefSwarm(OracleSwarm):
+    """N UavSystems of the reference's OWN source, compiled here against the Eigen/odeint stand-ins
+    (oracle/_ref/libref_uavsystem*.so, see oracle/ref_uavsystem.cpp).  Same harness as OracleSwarm;
+    stepping only — collisions, timeout synthesis and the ROS-wrapper rows are not part of UavSystem."""
+
+    def __init__(self, *a, flavour="default", **kw):
+        self._flavour = flavour
+        super().__init__(*a, **kw)
+
+    def _library(self):
+        L = refsys_lib(self._flavour)
+        if L is None:
+            raise RuntimeError("oracle/_ref/libref_uavsystem*.so not built (needs the reference tree: make -C oracle refsys)")
+        return L
+
+    def handle_collisions(self, *a, **kw):
+        raise NotImplementedError("UavSystem has no collision pass; see ref_nanoflann.cpp")
 
 
 def collide_snapshot(xyz, arm, prop, mass, crash_mode, rebounce, engine="port", n_threads=1, cap=None):

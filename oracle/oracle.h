@@ -1,8 +1,9 @@
 /* oracle/oracle.h — C interface of the CPU oracle (liboracle.so).  TEST INFRASTRUCTURE ONLY:
  * only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / `--impl reference` legs may
- * load it.  See uav_oracle.hpp for what is restated and why parity of the dynamics is UNPINNED
- * (the reference ships no tests and cannot be compiled here); the collision predicate is pinned
- * against the real vendored nanoflann by ref_nanoflann.cpp. */
+ * load it.  See uav_oracle.hpp for what is restated.  The dynamics are pinned bit for bit against
+ * the reference's own UavSystem sources compiled by ref_uavsystem.cpp (which exports the stepping
+ * subset of this interface under the same names); the collision predicate is pinned against the
+ * real vendored nanoflann by ref_nanoflann.cpp. */
 #ifndef ORACLE_H
 #define ORACLE_H
 #include <stdint.h>

@@ -1,12 +1,15 @@
 #!/usr/bin/env python
 """Generates the golden fixtures under tests/golden/.
 
-The reference ships no golden vectors and its UavSystem cannot be built in this image (no Eigen,
-no Boost), so the trajectory fixtures come from the CPU oracle restatement (oracle/uav_oracle.hpp)
-— they pin the ORACLE against accidental change and give the GPU path a fixed target; they are not
-independent evidence for the restatement itself.  The collision fixture, however,
-is produced by the reference's REAL vendored nanoflann (oracle/_ref/libref_nanoflann.so, built
-from /root/reference/include) and is therefore a reference-generated golden vector.
+The reference ships no golden vectors, so they are generated here from the reference itself:
+
+* trajectory fixtures (c1_position_x500.json, modes_2s.json) come from the reference's OWN
+  UavSystem sources compiled in this container (oracle/_ref/libref_uavsystem.so — uav_system.hpp,
+  multirotor_model.hpp and controllers/*.hpp from /root/reference/include, against the Eigen/odeint
+  stand-ins of oracle/shim because the image has neither library; see oracle/ref_uavsystem.cpp).
+  The generator also checks that the restated oracle reproduces every number bit for bit;
+* the collision fixture comes from the reference's REAL vendored nanoflann
+  (oracle/_ref/libref_nanoflann.so, built from /root/reference/include).
 
     python tests/golden/make_golden.py        # rewrites tests/golden/*.json
 """
@@ -40,11 +43,14 @@ def state_dict(st, i=0):
 
 def c1():
     """BASELINE config 1: x500, spawn (0,0,1) heading 0, PositionCmd (5,-3,4) heading 1.0, dt=0.005, 10 s."""
-    s = O.OracleSwarm([airframe("x500")], spawn_xyz=[[0, 0, 1]], spawn_heading=[0.0], n=1)
-    s.set_input(O.POSITION_CMD, [[5.0, -3.0, 4.0, 1.0]])
+    s, chk = (cls([airframe("x500")], spawn_xyz=[[0, 0, 1]], spawn_heading=[0.0], n=1) for cls in (O.RefSwarm, O.OracleSwarm))
     samples = []
+    for u in (s, chk):
+        u.set_input(O.POSITION_CMD, [[5.0, -3.0, 4.0, 1.0]])
     for sec in range(10):
         s.make_step(0.005, 200)
+        chk.make_step(0.005, 200)
+        assert state_dict(s.get_state()) == state_dict(chk.get_state()), "restated oracle differs from the compiled reference"
         samples.append({"t": sec + 1, **state_dict(s.get_state())})
     return {"config": "C1", "frame": "x500", "spawn": [0, 0, 1], "heading": 0.0, "cmd": [5.0, -3.0, 4.0, 1.0], "dt": 0.005, "samples": samples}
 
@@ -69,9 +75,11 @@ def modes():
     out = []
     for frame in ("x500", "f550", "naki"):
         for name, (mode, cmd) in MODE_CMDS.items():
-            s = O.OracleSwarm([airframe(frame)], spawn_xyz=[[1, 2, 5]], spawn_heading=[0.3], n=1)
-            s.set_input(mode, [cmd])
-            s.make_step(0.01, 200)
+            s, chk = (cls([airframe(frame)], spawn_xyz=[[1, 2, 5]], spawn_heading=[0.3], n=1) for cls in (O.RefSwarm, O.OracleSwarm))
+            for u in (s, chk):
+                u.set_input(mode, [cmd])
+                u.make_step(0.01, 200)
+            assert state_dict(s.get_state()) == state_dict(chk.get_state()), "restated oracle differs from the compiled reference"
             out.append({"frame": frame, "mode": name, "mode_id": mode, "cmd": cmd, "steps": 200, "dt": 0.01, **state_dict(s.get_state())})
     return {"spawn": [1, 2, 5], "heading": 0.3, "cases": out}
 
@@ -97,7 +105,10 @@ def collisions():
 if __name__ == "__main__":
     O.build()
     assert O.ref_lib() is not None, "oracle/_ref/libref_nanoflann.so is needed (build it where /root/reference exists)"
-    meta = {"generator": "tests/golden/make_golden.py", "oracle_git": git_hash()}
+    assert O.refsys_lib() is not None, "oracle/_ref/libref_uavsystem.so is needed (build it where /root/reference exists)"
+    meta = {"generator": "tests/golden/make_golden.py", "oracle_git": git_hash(),
+            "trajectories_from": "reference UavSystem sources compiled against oracle/shim (oracle/_ref/libref_uavsystem.so)",
+            "collisions_from": "reference nanoflann (oracle/_ref/libref_nanoflann.so)"}
     for name, fn in (("c1_position_x500", c1), ("modes_2s", modes), ("collisions_400", collisions)):
         doc = {"meta": meta, **fn()}
         with open(os.path.join(HERE, name + ".json"), "w") as f:

@@ -94,7 +94,7 @@ def test_product_never_touches_the_oracle():
         for f in files:
             if f.endswith((".py", ".cu", ".cpp", ".h", ".hpp", "Makefile")):
                 text = open(os.path.join(dirpath, f), errors="replace").read()
-                for pat in (r"^\s*(from|import)\s+oracle", r"#\s*include\s*[<\"][^>\"]*oracle", r"liboracle", r"libref_nanoflann", r"oracle/_"):
+                for pat in (r"^\s*(from|import)\s+oracle", r"#\s*include\s*[<\"][^>\"]*oracle", r"liboracle", r"libref_nanoflann", r"libref_uavsystem", r"oracle/_"):
                     assert not re.search(pat, text, flags=re.M), (os.path.join(dirpath, f), pat)
     from mrs_multirotor_simulator_b200 import _lib
 
