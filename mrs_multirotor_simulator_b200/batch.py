@@ -317,6 +317,13 @@ class UavBatch:
         check(self._L.mrsb_get_counters(self.h, _ptr(out)))
         return dict(steps=int(out[0]), collision_passes=int(out[1]), pairs=int(out[2]), crashed=int(out[3]), launches=int(out[4]))
 
+    def collision_info(self):
+        """How the collision pass is organised on this handle (diagnostics; results do not depend on it)."""
+        out = np.zeros(8, dtype=np.float64)
+        check(self._L.mrsb_get_collision_info(self.h, _ptr(out)))
+        return dict(cell=float(out[0]), neighbour_lists=bool(out[1]), list_radius=float(out[2]), skin=float(out[3]), passes=int(out[4]),
+                    rebuilds=int(out[5]), overflow_passes=int(out[6]), n_buckets=int(out[7]))
+
     # ---- sharded operation ----------------------------------------------------------------------
     @staticmethod
     def nccl_unique_id():

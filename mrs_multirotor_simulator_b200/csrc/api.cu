@@ -150,6 +150,14 @@ struct mrsb_sim {
   cudaGraphExec_t coll_graph[2]     = {nullptr, nullptr};
   int             coll_graph_own[2] = {0, 0};  // own kernels per replay (for the launch counter)
 
+  // neighbour lists (single-shard handles): the table rebuild sits in a conditional node of the graph
+  bool     lists_on            = false;
+  int      steps_since_pass    = 0;     // stepping launches since the last collision pass
+  bool     positions_touched   = true;  // positions were written by something else than ONE stepping launch
+  int      rebuild_own         = 0;     // own kernels of one rebuild (for the launch counter)
+  int64_t  rebuilds_counted    = 0;
+  uint32_t* h_one              = nullptr;  // pinned constant 1 (source of the async "force rebuild" copy)
+
   int64_t n_steps = 0, n_passes = 0, n_launches = 0;
 };
 
@@ -333,14 +341,32 @@ static int repoint(mrsb_sim* h, int64_t n, const int32_t* idx, Edit edit) {
 
 // Fused exchange set-up: a second gather buffer, this rank's flag slots, and IPC mappings of every
 // peer's two buffers and flags (handles travel through one NCCL all-gather of raw bytes).
+// Cell geometry of the spatial hash.  Handles that run the full pass every tick use the smallest cell
+// whose half covers the search radius sqrt(3) (4 m: fewest candidates).  Handles that keep neighbour
+// lists between rebuilds use a larger cell: the list radius is just under cell / 2, so a larger cell
+// buys a larger skin, i.e. fewer rebuilds for more candidates per rebuild.
+static void set_collision_geometry(mrsb_sim* h, bool lists) {
+  DevGrid& g  = h->grid;
+  h->lists_on = lists;
+  double cell = lists ? 6.0 : 4.0;
+  if (const char* e = getenv("MRSB_COLLISION_CELL")) cell = std::max(3.5, atof(e));
+  g.inv_cell = 1.0 / cell;
+  g.reach    = 0.5 * cell;
+  const double r_list = g.reach * (1.0 - 1e-6);
+  g.list_r2  = r_list * r_list;
+  g.skin     = (r_list - 1.7320508075688775) * (1.0 - 1e-6);
+  h->ds.disp_max       = lists ? &g.ctl->disp_max_bits : nullptr;
+  h->positions_touched = true;
+}
+
 static int setup_p2p(mrsb_sim* h) {
   const int    G     = h->n_ranks;
   const size_t bytes = sizeof(double) * 3 * size_t(h->ds.n_global);
   h->gbuf[0]         = h->ds.gpos;
   CU(cudaMalloc(&h->gbuf[1], std::max<size_t>(bytes, 16)));
   CU(cudaMemcpy(h->gbuf[1], h->gbuf[0], bytes, cudaMemcpyDeviceToDevice));
-  CU(cudaMalloc(&h->d_flags, sizeof(unsigned long long) * G));
-  CU(cudaMemset(h->d_flags, 0, sizeof(unsigned long long) * G));
+  CU(cudaMalloc(&h->d_flags, sizeof(unsigned long long) * 3 * G));  // epochs [G] + displacement words [2G] (step_kernel.cu)
+  CU(cudaMemset(h->d_flags, 0, sizeof(unsigned long long) * 3 * G));
   CU(cudaHostAlloc(&h->h_status, sizeof(int), cudaHostAllocMapped));
   *h->h_status = 0;
   struct Handles {
@@ -394,6 +420,8 @@ static int setup_p2p(mrsb_sim* h) {
   h->parity   = 0;
   h->ds.peers = nullptr;  // set per step
   h->p2p      = true;
+  // the hand-shake also carries every rank's displacement bound: neighbour lists work across shards
+  set_collision_geometry(h, h->grid.nl_count != nullptr);
   drop_collision_graphs(h);
   return MRSB_OK;
 }
@@ -431,11 +459,12 @@ int mrsb_destroy(mrsb_handle h) {
   for (void* p : {(void*)h->d_peers[0], (void*)h->d_peers[1], (void*)h->d_flags, (void*)h->d_peer_flags})
     if (p) cudaFree(p);
   if (h->h_status) cudaFreeHost(h->h_status);
+  if (h->h_one) cudaFreeHost(h->h_one);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   void* ptrs[] = {h->ds.st,     h->ds.vprev,  h->ds.rpm,      h->ds.pid,      h->ds.fext,         h->ds.mext,       h->ds.imu,    h->ds.initz,
                   h->ds.cmd,    h->ds.ff,     h->ds.flags,    h->ds.mode,     h->ds.gpos,         h->d_params,      h->d_pset,    h->d_stage,
                   h->d_idx,     h->grid.bucket, h->grid.rank, h->grid.count, h->grid.aabb, h->grid.begin, h->grid.rec, h->grid.pairs,
-                  h->grid.counters, h->cub_tmp};
+                  h->grid.counters, h->cub_tmp, h->grid.nl_count, h->grid.nl_items, h->grid.ctl};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -559,15 +588,27 @@ int mrsb_create(const mrsb_create_info* info, mrsb_handle* out) {
     g.n_buckets = 1u << bits;
     CREATE_RC(dalloc(&g.bucket, ng));
     CREATE_RC(dalloc(&g.rank, ng));
-    CREATE_RC(dalloc(&g.count, size_t(g.n_buckets) + 2));  // + mirror of bucket 0 + sentinel
-    CREATE_RC(dalloc(&g.begin, size_t(g.n_buckets) + 2));
+    CREATE_RC(dalloc(&g.count, size_t(g.n_buckets) + 4));  // + mirrors of buckets 0 and 1 + sentinel
+    CREATE_RC(dalloc(&g.begin, size_t(g.n_buckets) + 4));
     CREATE_RC(dalloc(&g.aabb, 6));
     CREATE_RC(dalloc(&g.rec, 2 * ng));  // worst case: every UAV in bucket 0 and mirrored
     g.pair_cap = int64_t(std::max<size_t>(4096, 4 * size_t(std::max<int64_t>(s.n, 1))));
     CREATE_RC(dalloc(&g.pairs, 2 * size_t(g.pair_cap)));
     CREATE_RC(dalloc(&g.counters, 4));
-    h->cub_tmp_bytes = collide_tmp_bytes(int64_t(g.n_buckets) + 2);
+    h->cub_tmp_bytes = collide_tmp_bytes(int64_t(g.n_buckets) + 3);
     CREATE_CU(cudaMalloc(&h->cub_tmp, std::max<size_t>(h->cub_tmp_bytes, 16)));
+    // neighbour lists: single-shard handles now, sharded ones once the fused exchange is up (setup_p2p)
+    if (s.n > 0 && !getenv("MRSB_NO_NEIGHBOUR_LISTS")) {
+      g.nl_ld = s.ld;
+      CREATE_RC(dalloc(&g.nl_count, size_t(g.nl_ld)));
+      CREATE_RC(dalloc(&g.nl_items, size_t(MRSB_NL_CAP) * size_t(g.nl_ld)));
+      CREATE_RC(dalloc(&g.ctl, 1));
+      CREATE_CU(cudaMemsetAsync(g.ctl, 0, sizeof(NlCtl), h->stream));
+      CREATE_CU(cudaHostAlloc(&h->h_one, 2 * sizeof(uint32_t), cudaHostAllocDefault));
+      h->h_one[0] = 1u;
+      h->h_one[1] = 0xFFFFFFFFu;  // "unbounded displacement"
+    }
+    set_collision_geometry(h, g.nl_count != nullptr && s.n_global == s.n);
   }
   h->shard_begin_of = {s.shard_begin};
   h->shard_count_of = {s.n};
@@ -796,10 +837,12 @@ static int exchange_positions(mrsb_sim* h) {
   if (h->p2p && h->pushed) {
     // the step kernel already stored this shard's positions into every peer's buffer: only the
     // hand-shake "my epoch has landed" / "everybody's has" is left
-    h->n_launches += launch_p2p_signal(h->d_peer_flags, h->n_ranks, h->rank, h->epoch, h->stream);
-    h->n_launches += launch_p2p_wait(h->d_flags, h->n_ranks, h->rank, h->epoch, h->h_status, h->stream);
+    uint32_t* disp = h->lists_on ? &h->grid.ctl->disp_max_bits : nullptr;
+    h->n_launches += launch_p2p_signal(h->d_peer_flags, h->n_ranks, h->rank, h->epoch, disp, h->stream);
+    h->n_launches += launch_p2p_wait(h->d_flags, h->n_ranks, h->rank, h->epoch, h->h_status, disp, h->stream);
     return MRSB_OK;
   }
+  h->positions_touched = true;  // all-gather without the hand-shake: no swarm-wide displacement bound for this pass
   double* buf = h->ds.gpos;
   if (h->equal_shards) {
     NC(g_nccl.AllGather(buf + 3 * h->ds.shard_begin, buf, size_t(3 * h->ds.n), ncclDouble, h->comm, h->stream));
@@ -814,8 +857,74 @@ static int exchange_positions(mrsb_sim* h) {
   return MRSB_OK;
 }
 
+// The pass with neighbour lists as ONE graph:  decide -> IF (rebuild) { table, lists } -> check.
+// The IF node's condition is set on the device by decide_kernel (cudaGraphSetConditional).
+static cudaGraphExec_t build_list_graph(mrsb_sim* h, int* own_fixed, int* own_rebuild) {
+  cudaGraph_t     graph = nullptr;
+  cudaGraphExec_t exec  = nullptr;
+  cudaStream_t    side  = nullptr;
+  bool            ok    = false;
+  if (cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  do {
+    cudaStreamCaptureStatus status;
+    const cudaGraphNode_t*  deps  = nullptr;
+    size_t                  n_dep = 0;
+    if (cudaStreamGetCaptureInfo_v2(h->stream, &status, nullptr, &graph, &deps, &n_dep) != cudaSuccess || !graph) break;
+    cudaGraphConditionalHandle handle;
+    if (cudaGraphConditionalHandleCreate(&handle, graph, 0, cudaGraphCondAssignDefault) != cudaSuccess) break;
+    *own_fixed = launch_collide_decide(h->grid, 0, handle, 1, h->stream);
+    if (cudaStreamGetCaptureInfo_v2(h->stream, &status, nullptr, &graph, &deps, &n_dep) != cudaSuccess) break;
+    cudaGraphNodeParams cp = {};
+    cp.type                = cudaGraphNodeTypeConditional;
+    cp.conditional.handle  = handle;
+    cp.conditional.type    = cudaGraphCondTypeIf;
+    cp.conditional.size    = 1;
+    cudaGraphNode_t cond   = nullptr;
+    if (cudaGraphAddNode(&cond, graph, deps, n_dep, &cp) != cudaSuccess) break;
+    cudaGraph_t body = cp.conditional.phGraph_out[0];
+    if (cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking) != cudaSuccess) break;
+    if (cudaStreamBeginCaptureToGraph(side, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal) != cudaSuccess) break;
+    *own_rebuild = launch_collide_rebuild(h->ds, h->grid, h->coll_crash, h->coll_rebounce, h->cub_tmp, h->cub_tmp_bytes, side);
+    cudaGraph_t body_out = nullptr;
+    if (cudaStreamEndCapture(side, &body_out) != cudaSuccess) break;
+    if (cudaStreamUpdateCaptureDependencies(h->stream, &cond, 1, cudaStreamSetCaptureDependencies) != cudaSuccess) break;
+    *own_fixed += launch_collide_check(h->ds, h->grid, h->coll_crash, h->coll_rebounce, h->stream);
+    ok = true;
+  } while (false);
+  cudaGraph_t captured = nullptr;
+  const bool  ended    = cudaStreamEndCapture(h->stream, &captured) == cudaSuccess && captured;
+  if (ok && ended && cudaGraphInstantiate(&exec, captured, 0) != cudaSuccess) exec = nullptr;
+  if (captured) cudaGraphDestroy(captured);
+  if (side) cudaStreamDestroy(side);
+  cudaGetLastError();
+  return exec;
+}
+
 static int collide_local(mrsb_sim* h) {
   const int k = h->p2p ? h->parity : 0;
+  if (h->lists_on) {
+    // anything but exactly one stepping launch since the last pass: the displacement bound does not cover it
+    if (h->positions_touched || h->steps_since_pass != 1)
+      CU(cudaMemcpyAsync(&h->grid.ctl->force, h->h_one, sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+    h->positions_touched = false;
+    h->steps_since_pass  = 0;
+    if (!h->coll_graph[k] && !getenv("MRSB_NO_GRAPH")) h->coll_graph[k] = build_list_graph(h, &h->coll_graph_own[k], &h->rebuild_own);
+    if (h->coll_graph[k]) {
+      CU(cudaGraphLaunch(h->coll_graph[k], h->stream));
+      h->n_launches += h->coll_graph_own[k];  // the rebuilds are added from the device-side count (mrsb_get_counters)
+    } else {
+      // no graph (MRSB_NO_GRAPH, or conditional nodes unavailable): rebuild every pass
+      h->n_launches += launch_collide_decide(h->grid, 1, cudaGraphConditionalHandle{}, 0, h->stream);
+      h->rebuild_own = launch_collide_rebuild(h->ds, h->grid, h->coll_crash, h->coll_rebounce, h->cub_tmp, h->cub_tmp_bytes, h->stream);
+      h->n_launches += launch_collide_check(h->ds, h->grid, h->coll_crash, h->coll_rebounce, h->stream);
+    }
+    h->n_passes++;
+    CU(cudaGetLastError());
+    return MRSB_OK;
+  }
   if (!h->coll_graph[k] && !getenv("MRSB_NO_GRAPH")) {
     cudaGraph_t graph = nullptr;
     if (cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
@@ -855,6 +964,7 @@ int mrsb_make_step(mrsb_handle h, double dt, int32_t k_substeps) {
   h->n_launches += launch_step(h->ds, h->uniform_pset >= 0 ? &h->uniform_params : nullptr, dt, k_substeps, h->uniform_mode, h->uniform_nm,
                                h->any_moment, h->stream);
   h->n_steps += k_substeps;
+  h->steps_since_pass++;
   CU(cudaGetLastError());
   return MRSB_OK;
 }
@@ -865,6 +975,10 @@ int mrsb_handle_collisions(mrsb_handle h) {
   int rc = flush_params(h);
   if (rc) return rc;
   if (h->ds.n_global > h->ds.n && h->n_ranks <= 1) return fail(MRSB_ERR_STATE, "sharded handle without communicator");
+  if (h->lists_on && (h->positions_touched || h->steps_since_pass != 1))
+    // anything but exactly one stepping launch since the last pass: this rank's displacement is unbounded —
+    // said through the displacement word, so that every peer rebuilds as well
+    CU(cudaMemcpyAsync(&h->grid.ctl->disp_max_bits, h->h_one + 1, sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
   rc = exchange_positions(h);
   if (rc) return rc;
   return collide_local(h);
@@ -941,7 +1055,8 @@ int mrsb_set_state(mrsb_handle h, int64_t n, const int32_t* idx, const double* x
   if (motor_rpm && !rc) rc = put_rows(h, h->ds.rpm, MRSB_NM, 0, MRSB_NM, n, idx, motor_rpm, MRSB_NM, 0);
   if (x && !rc) {
     h->n_launches += launch_publish_positions(h->ds, h->stream);
-    h->pushed = false;
+    h->pushed            = false;
+    h->positions_touched = true;
   }
   return rc;
 }
@@ -960,6 +1075,7 @@ int mrsb_set_state_pos(mrsb_handle h, int64_t n, const int32_t* idx, const doubl
   CU(cudaMemcpyAsync(d_xyz, xyz, sizeof(double) * 3 * size_t(n), cudaMemcpyHostToDevice, h->stream));
   CU(cudaMemcpyAsync(d_hdg, heading, sizeof(double) * size_t(n), cudaMemcpyHostToDevice, h->stream));
   h->n_launches += launch_set_state_pos(h->ds, n, d_idx, d_xyz, d_hdg, h->stream);
+  h->positions_touched = true;
   h->pushed = false;
   CU(cudaGetLastError());
   return MRSB_OK;
@@ -1276,11 +1392,34 @@ int mrsb_get_counters(mrsb_handle h, int64_t* out5) {
   if (rc) return rc;
   int64_t crashed = 0;
   for (uint32_t f : fl) crashed += (f & FLAG_CRASHED) ? 1 : 0;
+  if (h->lists_on) {
+    // table rebuilds happen inside the graph's conditional node: count their kernels from the device-side tally
+    NlCtl ctl;
+    CU(cudaMemcpy(&ctl, h->grid.ctl, sizeof(ctl), cudaMemcpyDeviceToHost));
+    h->n_launches += (int64_t(ctl.n_rebuilds) - h->rebuilds_counted) * h->rebuild_own;
+    h->rebuilds_counted = int64_t(ctl.n_rebuilds);
+  }
   out5[0] = h->n_steps;
   out5[1] = h->n_passes;
   out5[2] = int64_t(found);
   out5[3] = crashed;
   out5[4] = h->n_launches;
+  return MRSB_OK;
+}
+
+int mrsb_get_collision_info(mrsb_handle h, double* out8) {
+  GUARD(h);
+  CU(cudaStreamSynchronize(h->stream));
+  NlCtl ctl{};
+  if (h->lists_on) CU(cudaMemcpy(&ctl, h->grid.ctl, sizeof(ctl), cudaMemcpyDeviceToHost));
+  out8[0] = 1.0 / h->grid.inv_cell;
+  out8[1] = h->lists_on ? 1.0 : 0.0;
+  out8[2] = h->lists_on ? std::sqrt(h->grid.list_r2) : 0.0;
+  out8[3] = h->lists_on ? h->grid.skin : 0.0;
+  out8[4] = double(ctl.n_passes);
+  out8[5] = double(ctl.n_rebuilds);
+  out8[6] = double(ctl.n_overflow_passes);
+  out8[7] = double(h->grid.n_buckets);
   return MRSB_OK;
 }
 
@@ -1353,7 +1492,8 @@ int mrsb_gather_buffer(mrsb_handle h, void** device_ptr, size_t* bytes) {
 
 int mrsb_publish_positions(mrsb_handle h) {
   GUARD(h);
-  h->pushed = false;
+  h->pushed            = false;
+  h->positions_touched = true;
   h->n_launches += launch_publish_positions(h->ds, h->stream);
   CU(cudaGetLastError());
   return MRSB_OK;

@@ -29,6 +29,20 @@
 // results are: pair lists are sorted on retrieval, and force sums of >= 3 terms are re-accumulated
 // in ascending j (sums of <= 2 terms are order-independent bit for bit).
 //
+// Neighbour lists (single-shard handles).  A UAV moves centimetres per tick, so the table is not
+// rebuilt every tick: a rebuild also records, for every UAV, the indices of all UAVs within
+// R_list = sqrt(3) + skin of it (<= NL_CAP of them, slot-major [slot][uav]).  The stepping kernel
+// reports the largest displacement of any UAV per launch (DevState::disp_max); `decide_kernel` sums
+// these bounds into D and the lists stay valid while 2 D <= skin (two UAVs now closer than sqrt(3)
+// were closer than sqrt(3) + 2 D when the lists were built).  On such ticks the pass is ONE kernel
+// (`check_kernel`: the exact predicate on the current positions of the listed candidates); the
+// rebuild (count/scan/scatter/build) sits in the body of a CUDA-graph conditional IF node whose
+// condition `decide_kernel` sets on the device, so no host round trip is involved.  Results are the
+// same bits either way: the lists only choose which pairs are tested.  Anything that moves UAVs
+// other than one stepping launch (set_state, publish_positions, several launches between passes)
+// forces a rebuild; a UAV with more than NL_CAP candidates switches the pass back to the full
+// `collide_kernel` until the crowd dissolves.  Sharded handles always run the full pass.
+//
 // Crash mode (SIM:347-348) marks the NEIGHBOUR crashed.  A shard must not write remote state, so the
 // owner of i evaluates the mirrored test d2 < ((arm_j+prop_j)+arm_i)+prop_i — the exact threshold
 // the owner of j uses for the directed pair (j,i) — and marks i itself.
@@ -40,14 +54,10 @@ namespace {
 
 #define DEV __device__ __forceinline__
 
-constexpr double kInvCell = 0.25;  // 4 m cells
-constexpr double kReach   = 2.0;   // > sqrt(3.0), exactly representable
-
-DEV int cell_of(double v) {
-  // floor(v / 4 m) saturated to +-2^29 (NaN -> 0); v * 0.25 is exact
-  double c = floor(v * kInvCell);
-  c        = fmin(fmax(c, -536870912.0), 536870912.0);
-  return (c == c) ? int(c) : 0;
+DEV int cell_of(double v, double inv_cell) {
+  // floor(v / cell): one F2I.FLOOR — saturates to INT_MIN / INT_MAX, NaN -> 0.  Monotone in v, and the
+  // SAME function files a record (count_kernel) and looks for it, which is all the stencil needs.
+  return __double2int_rd(__dmul_rn(v, inv_cell));
 }
 
 DEV uint32_t row_hash(int cy, int cz) {
@@ -98,8 +108,8 @@ __global__ void __launch_bounds__(256) box_kernel(const double* __restrict__ gpo
 }
 
 __global__ void __launch_bounds__(256) count_kernel(const double* __restrict__ gpos, int64_t n, int64_t shard_begin, int64_t n_local, int filter,
-                                                    const unsigned long long* __restrict__ aabb, uint32_t mask, uint32_t* __restrict__ count,
-                                                    uint32_t* __restrict__ bucket, uint32_t* __restrict__ rank) {
+                                                    const unsigned long long* __restrict__ aabb, uint32_t mask, double inv_cell, double reach,
+                                                    uint32_t* __restrict__ count, uint32_t* __restrict__ bucket, uint32_t* __restrict__ rank) {
   const int64_t j = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (j >= n) return;
   const double* p = gpos + 3 * j;
@@ -108,20 +118,20 @@ __global__ void __launch_bounds__(256) count_kernel(const double* __restrict__ g
     const int64_t l = j - shard_begin;
     if (l < 0 || l >= n_local) {
       // remote: keep it only if it can reach this shard's box (NaN compares false -> kept)
-      const bool out = x < dec(aabb[0]) - kReach || y < dec(aabb[1]) - kReach || z < dec(aabb[2]) - kReach || x > dec(aabb[3]) + kReach ||
-                       y > dec(aabb[4]) + kReach || z > dec(aabb[5]) + kReach;
+      const bool out = x < dec(aabb[0]) - reach || y < dec(aabb[1]) - reach || z < dec(aabb[2]) - reach || x > dec(aabb[3]) + reach ||
+                       y > dec(aabb[4]) + reach || z > dec(aabb[5]) + reach;
       if (out) {
         bucket[j] = 0xFFFFFFFFu;
         return;
       }
     }
   }
-  const uint32_t b = (row_hash(cell_of(y), cell_of(z)) + uint32_t(cell_of(x))) & mask;
+  const uint32_t b = (row_hash(cell_of(y, inv_cell), cell_of(z, inv_cell)) + uint32_t(cell_of(x, inv_cell))) & mask;
   bucket[j]        = b;
   rank[j]          = atomicAdd(&count[b], 1u);
-  // bucket B = mask+1 mirrors bucket 0 (same records, same ranks), so that the two x-adjacent cells
-  // of a stencil row are ALWAYS adjacent buckets, also across the end of the table
-  if (b == 0u) atomicAdd(&count[mask + 1u], 1u);
+  // buckets B and B+1 (B = mask+1) mirror buckets 0 and 1 (same records, same ranks), so that the
+  // x-adjacent cells of a stencil row are ALWAYS adjacent buckets, also across the end of the table
+  if (b <= 1u) atomicAdd(&count[mask + 1u + b], 1u);
 }
 
 __global__ void __launch_bounds__(256) scatter_kernel(const double* __restrict__ gpos, int64_t n, const uint32_t* __restrict__ bucket,
@@ -135,7 +145,7 @@ __global__ void __launch_bounds__(256) scatter_kernel(const double* __restrict__
   const double4  r = make_double4(q[0], q[1], q[2], __longlong_as_double((long long)j));
   const uint32_t k = rank[j];
   rec[begin[b] + k] = r;
-  if (b == 0u) rec[begin[n_buckets] + k] = r;  // mirror of bucket 0
+  if (b <= 1u) rec[begin[n_buckets + b] + k] = r;  // mirrors of buckets 0 and 1
 }
 
 // nanoflann L2 metric for dim 3, no contraction
@@ -147,40 +157,98 @@ DEV double nf_dist2(double ax, double ay, double az, double bx, double by, doubl
   return r;
 }
 
+// The <= 4 stencil rows around q.  The search ball (radius < reach = cell / 2) fits into two cells
+// per axis: {c0, c0 + 1} with c0 = cell_of(q - reach) — for any p with |p - q| < r_search,
+// q - reach <= p < (q - reach) + cell, and cell_of is monotone.  Each row (cy, cz) is ONE record
+// range: buckets b0, b0 + 1 with b0 = bucket of (cx0, cy, cz).
+struct Stencil {
+  int      rcy[4], rcz[4];
+  uint32_t lo[4], hi[4];
+};
+DEV Stencil stencil_of(const DevGrid& g, double qx, double qy, double qz) {
+  Stencil        st;
+  const uint32_t mask = g.n_buckets - 1;
+  const int      cx0 = cell_of(qx - g.reach, g.inv_cell), cy0 = cell_of(qy - g.reach, g.inv_cell), cz0 = cell_of(qz - g.reach, g.inv_cell);
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    st.rcy[k]         = cy0 + (k & 1);
+    st.rcz[k]         = cz0 + ((k >> 1) & 1);
+    const uint32_t b0 = (row_hash(st.rcy[k], st.rcz[k]) + uint32_t(cx0)) & mask;
+    st.lo[k]          = g.begin[b0];
+    st.hi[k]          = g.begin[b0 + 2];  // b0 + 2 <= mask + 2: begin[] has the two mirror buckets and a sentinel
+  }
+  return st;
+}
+
+// One accepted candidate (d2 < 3.0 already established): SIM:342-353 for the directed pair (i, j).
+struct PairAcc {
+  double fx = 0.0, fy = 0.0, fz = 0.0;
+  bool   crashed_me = false;
+};
+DEV void process_pair(const DevState& s, const DevGrid& g, int crash_mode, double rebounce, int64_t gi, double qx, double qy, double qz,
+                      const DevParams* __restrict__ Pi, int64_t gj, double rx_, double ry_, double rz_, PairAcc& acc) {
+  const double ai = Pi->arm_length, pi_ = Pi->prop_radius, mi = Pi->mass;
+  const double api = __dadd_rn(ai, pi_);
+  const double d2  = nf_dist2(qx, qy, qz, rx_, ry_, rz_);
+  const DevParams* __restrict__ Pj = s.params + s.pset[gj];
+  const double aj = Pj->arm_length, pj = Pj->prop_radius;
+  const double crit_ij = __dadd_rn(__dadd_rn(api, aj), pj);  // SIM:342
+  if (d2 < crit_ij) {                                         // SIM:346
+    const unsigned long long slot = atomicAdd(g.counters, 1ull);
+    if (slot < (unsigned long long)g.pair_cap) {
+      g.pairs[2 * slot]     = int32_t(gi);
+      g.pairs[2 * slot + 1] = int32_t(gj);
+    }
+    if (!crash_mode) {
+      // rebounce * normalized(x_i - x_j) * m_i * (m_j / (m_i + m_j))   (SIM:350), Eigen evaluation order
+      const double rx = __dsub_rn(qx, rx_), ry = __dsub_rn(qy, ry_), rz = __dsub_rn(qz, rz_);
+      const double z  = __dadd_rn(__dmul_rn(rx, rx), __dadd_rn(__dmul_rn(ry, ry), __dmul_rn(rz, rz)));
+      double       nx = rx, ny = ry, nz = rz;
+      if (z > 0.0) {
+        const double sq = __dsqrt_rn(z);
+        nx              = __ddiv_rn(rx, sq);
+        ny              = __ddiv_rn(ry, sq);
+        nz              = __ddiv_rn(rz, sq);
+      }
+      const double mj = Pj->mass;
+      const double wt = __ddiv_rn(mj, __dadd_rn(mi, mj));
+      acc.fx          = __dadd_rn(acc.fx, __dmul_rn(__dmul_rn(__dmul_rn(rebounce, nx), mi), wt));
+      acc.fy          = __dadd_rn(acc.fy, __dmul_rn(__dmul_rn(__dmul_rn(rebounce, ny), mi), wt));
+      acc.fz          = __dadd_rn(acc.fz, __dmul_rn(__dmul_rn(__dmul_rn(rebounce, nz), mi), wt));
+    }
+  }
+  if (crash_mode) {
+    const double crit_ji = __dadd_rn(__dadd_rn(__dadd_rn(aj, pj), ai), pi_);  // threshold of the directed pair (j,i)
+    if (d2 < crit_ji) acc.crashed_me = true;
+  }
+}
+
+// SIM:356-358: forces replace external_force_ for the next tick (zero in crash mode, SIM:315-319)
+DEV void store_result(const DevState& s, int64_t li, const PairAcc& acc) {
+  s.fext[tix(F3_ROWS, 0, li)] = acc.fx;
+  s.fext[tix(F3_ROWS, 1, li)] = acc.fy;
+  s.fext[tix(F3_ROWS, 2, li)] = acc.fz;
+  if (acc.crashed_me) s.flags[li] |= FLAG_CRASHED;
+}
+
 #ifndef MRSB_COLLIDE_MINB
 #define MRSB_COLLIDE_MINB 7  // 71 registers, no spills; 8 and 10 (64 / 48 registers) measured no faster
 #endif
-__global__ void __launch_bounds__(128, MRSB_COLLIDE_MINB) collide_kernel(DevState s, DevGrid g, int crash_mode, double rebounce) {
+// The full pass: every record against its stencil.  `only_if`: nullptr, or a device word that must
+// be non-zero for the kernel to do anything (the neighbour-list overflow fall-back).
+__global__ void __launch_bounds__(128, MRSB_COLLIDE_MINB) collide_kernel(DevState s, DevGrid g, int crash_mode, double rebounce, const uint32_t* only_if) {
+  if (only_if && *only_if == 0u) return;
   const int64_t p = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (p >= int64_t(g.begin[g.n_buckets])) return;  // beyond the primary records (the mirror bucket holds copies)
+  if (p >= int64_t(g.begin[g.n_buckets])) return;  // beyond the primary records (the mirror buckets hold copies)
   const double4 q  = g.rec[p];
   const int64_t gi = __double_as_longlong(q.w);
   const int64_t li = gi - s.shard_begin;
   if (li < 0 || li >= s.n) return;  // halo record: its owner handles it
 
-  // the <= 4 stencil rows (cy0..cy1) x (cz0..cz1) around q; each is ONE record range cx0..cx1
-  const uint32_t mask = g.n_buckets - 1;
-  const int      cx0 = cell_of(q.x - kReach), cx1 = cell_of(q.x + kReach);
-  const int      cy0 = cell_of(q.y - kReach), cy1 = cell_of(q.y + kReach);
-  const int      cz0 = cell_of(q.z - kReach), cz1 = cell_of(q.z + kReach);
-  const uint32_t w   = uint32_t(cx1 - cx0) + 1u;  // 1 or 2 buckets
-  int            rcy[4], rcz[4];
-  uint32_t       lo[4], hi[4];
-  double4        first[4];
+  const Stencil st = stencil_of(g, q.x, q.y, q.z);
+  double4       first[4];
 #pragma unroll
-  for (int k = 0; k < 4; k++) {
-    rcy[k]        = (k & 1) ? cy1 : cy0;
-    rcz[k]        = (k & 2) ? cz1 : cz0;
-    const bool on = (!(k & 1) || cy1 != cy0) && (!(k & 2) || cz1 != cz0);
-    lo[k] = hi[k] = 0u;
-    if (on) {
-      const uint32_t b0 = (row_hash(rcy[k], rcz[k]) + uint32_t(cx0)) & mask;
-      lo[k]             = g.begin[b0];
-      hi[k]             = g.begin[b0 + w];  // b0 + w <= mask + 2: begin[] has the mirror bucket and a sentinel
-    }
-  }
-#pragma unroll
-  for (int k = 0; k < 4; k++) first[k] = lo[k] < hi[k] ? g.rec[lo[k]] : q;  // the four leading candidates are fetched together
+  for (int k = 0; k < 4; k++) first[k] = st.lo[k] < st.hi[k] ? g.rec[st.lo[k]] : q;  // the four leading candidates are fetched together
 
   // ---- phase 1 (cheap, unrolled): which records are in the search ball?  A record r found in row k
   // is a genuine, not-yet-seen neighbour iff d2 < 3.0 AND its own cell row is row k (rejects bucket
@@ -189,7 +257,7 @@ __global__ void __launch_bounds__(128, MRSB_COLLIDE_MINB) collide_kernel(DevStat
     if (__double_as_longlong(r.w) == gi) return false;  // SIM:335
     const double d2 = nf_dist2(q.x, q.y, q.z, r.x, r.y, r.z);
     if (!(d2 < 3.0)) return false;  // NF:305-309
-    return cell_of(r.y) == rcy[k] && cell_of(r.z) == rcz[k];
+    return cell_of(r.y, g.inv_cell) == st.rcy[k] && cell_of(r.z, g.inv_cell) == st.rcz[k];
   };
   int      n_ball = 0;
   uint32_t h0 = 0, h1 = 0;
@@ -200,55 +268,18 @@ __global__ void __launch_bounds__(128, MRSB_COLLIDE_MINB) collide_kernel(DevStat
   };
 #pragma unroll
   for (int k = 0; k < 4; k++) {
-    if (lo[k] < hi[k]) {
-      if (in_ball(first[k], k)) note(lo[k]);
-      for (uint32_t t = lo[k] + 1; t < hi[k]; t++)
+    if (st.lo[k] < st.hi[k]) {
+      if (in_ball(first[k], k)) note(st.lo[k]);
+      for (uint32_t t = st.lo[k] + 1; t < st.hi[k]; t++)
         if (in_ball(g.rec[t], k)) note(t);
     }
   }
 
-  double fx = 0.0, fy = 0.0, fz = 0.0;
-  bool   crashed_me = false;
+  PairAcc acc;
   if (n_ball > 0) {
     // ---- phase 2 (rare, one copy of the heavy code): thresholds, pair list, force, crash flag
     const DevParams* __restrict__ Pi = s.params + s.pset[gi];
-    const double ai = Pi->arm_length, pi_ = Pi->prop_radius, mi = Pi->mass;
-    const double api = __dadd_rn(ai, pi_);
-    auto process = [&](const double4& r) {
-      const int64_t gj = __double_as_longlong(r.w);
-      const double  d2 = nf_dist2(q.x, q.y, q.z, r.x, r.y, r.z);
-      const DevParams* __restrict__ Pj = s.params + s.pset[gj];
-      const double aj = Pj->arm_length, pj = Pj->prop_radius;
-      const double crit_ij = __dadd_rn(__dadd_rn(api, aj), pj);  // SIM:342
-      if (d2 < crit_ij) {                                         // SIM:346
-        const unsigned long long slot = atomicAdd(g.counters, 1ull);
-        if (slot < (unsigned long long)g.pair_cap) {
-          g.pairs[2 * slot]     = int32_t(gi);
-          g.pairs[2 * slot + 1] = int32_t(gj);
-        }
-        if (!crash_mode) {
-          // rebounce * normalized(x_i - x_j) * m_i * (m_j / (m_i + m_j))   (SIM:350), Eigen evaluation order
-          const double rx = __dsub_rn(q.x, r.x), ry = __dsub_rn(q.y, r.y), rz = __dsub_rn(q.z, r.z);
-          const double z  = __dadd_rn(__dmul_rn(rx, rx), __dadd_rn(__dmul_rn(ry, ry), __dmul_rn(rz, rz)));
-          double       nx = rx, ny = ry, nz = rz;
-          if (z > 0.0) {
-            const double sq = __dsqrt_rn(z);
-            nx              = __ddiv_rn(rx, sq);
-            ny              = __ddiv_rn(ry, sq);
-            nz              = __ddiv_rn(rz, sq);
-          }
-          const double mj = Pj->mass;
-          const double wt = __ddiv_rn(mj, __dadd_rn(mi, mj));
-          fx              = __dadd_rn(fx, __dmul_rn(__dmul_rn(__dmul_rn(rebounce, nx), mi), wt));
-          fy              = __dadd_rn(fy, __dmul_rn(__dmul_rn(__dmul_rn(rebounce, ny), mi), wt));
-          fz              = __dadd_rn(fz, __dmul_rn(__dmul_rn(__dmul_rn(rebounce, nz), mi), wt));
-        }
-      }
-      if (crash_mode) {
-        const double crit_ji = __dadd_rn(__dadd_rn(__dadd_rn(aj, pj), ai), pi_);  // threshold of the directed pair (j,i)
-        if (d2 < crit_ji) crashed_me = true;
-      }
-    };
+    auto process = [&](const double4& r) { process_pair(s, g, crash_mode, rebounce, gi, q.x, q.y, q.z, Pi, __double_as_longlong(r.w), r.x, r.y, r.z, acc); };
     if (n_ball <= 2) {
       // sums of <= 2 terms do not depend on the order
       for (int c = 0; c < n_ball; c++) {
@@ -263,7 +294,7 @@ __global__ void __launch_bounds__(128, MRSB_COLLIDE_MINB) collide_kernel(DevStat
         int64_t  best = INT64_MAX;
         uint32_t bt   = 0;
         for (int k = 0; k < 4; k++) {
-          for (uint32_t t = lo[k]; t < hi[k]; t++) {
+          for (uint32_t t = st.lo[k]; t < st.hi[k]; t++) {
             const double4 r  = g.rec[t];
             const int64_t gj = __double_as_longlong(r.w);
             if (gj <= last || gj >= best || !in_ball(r, k)) continue;
@@ -277,12 +308,117 @@ __global__ void __launch_bounds__(128, MRSB_COLLIDE_MINB) collide_kernel(DevStat
       }
     }
   }
+  store_result(s, li, acc);
+}
 
-  // SIM:356-358: forces replace external_force_ for the next tick (zero in crash mode, SIM:315-319)
-  s.fext[tix(F3_ROWS, 0, li)] = fx;
-  s.fext[tix(F3_ROWS, 1, li)] = fy;
-  s.fext[tix(F3_ROWS, 2, li)] = fz;
-  if (crashed_me) s.flags[li] |= FLAG_CRASHED;
+// ---- neighbour lists ---------------------------------------------------------------------------
+
+// One thread per record: every other record within the list radius goes into the UAV's list.
+__global__ void __launch_bounds__(128, MRSB_COLLIDE_MINB) build_lists_kernel(DevState s, DevGrid g) {
+  const int64_t p = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (p >= int64_t(g.begin[g.n_buckets])) return;
+  const double4 q  = g.rec[p];
+  const int64_t gi = __double_as_longlong(q.w);
+  const int64_t li = gi - s.shard_begin;
+  if (li < 0 || li >= s.n) return;
+  const Stencil st = stencil_of(g, q.x, q.y, q.z);
+  double4       first[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) first[k] = st.lo[k] < st.hi[k] ? g.rec[st.lo[k]] : q;
+  uint32_t cnt  = 0;
+  auto     take = [&](const double4& r, int k) {
+    const int64_t gj = __double_as_longlong(r.w);
+    if (gj == gi) return;
+    const double d2 = nf_dist2(q.x, q.y, q.z, r.x, r.y, r.z);
+    if (!(d2 < g.list_r2)) return;
+    if (cell_of(r.y, g.inv_cell) != st.rcy[k] || cell_of(r.z, g.inv_cell) != st.rcz[k]) return;  // bucket alias / duplicate
+    if (cnt < MRSB_NL_CAP) g.nl_items[int64_t(cnt) * g.nl_ld + li] = int32_t(gj);
+    cnt++;
+  };
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    if (st.lo[k] < st.hi[k]) {
+      take(first[k], k);
+      for (uint32_t t = st.lo[k] + 1; t < st.hi[k]; t++) take(g.rec[t], k);
+    }
+  }
+  g.nl_count[li] = min(cnt, uint32_t(MRSB_NL_CAP));
+  if (cnt > MRSB_NL_CAP) {  // too crowded for the lists: this pass and the next ones run the full kernel
+    g.ctl->overflow = 1u;
+    g.ctl->valid    = 0u;
+  }
+}
+
+// One thread per UAV: the exact predicate on the CURRENT positions of the listed candidates.
+__global__ void __launch_bounds__(256) check_kernel(DevState s, DevGrid g, int crash_mode, double rebounce) {
+  if (g.ctl->overflow) return;  // collide_kernel did this pass
+  const int64_t li = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (li >= s.n) return;
+  const uint32_t cnt = g.nl_count[li];
+  PairAcc        acc;
+  if (cnt) {
+    const int64_t gi = li + s.shard_begin;
+    const double* qp = s.gpos + 3 * gi;
+    const double  qx = qp[0], qy = qp[1], qz = qp[2];
+    uint32_t      hits = 0;
+    for (uint32_t c = 0; c < cnt; c++) {
+      const double* rp = s.gpos + 3 * int64_t(g.nl_items[int64_t(c) * g.nl_ld + li]);
+      if (nf_dist2(qx, qy, qz, rp[0], rp[1], rp[2]) < 3.0) hits |= 1u << c;  // NF:305-309
+    }
+    if (hits) {
+      const DevParams* __restrict__ Pi = s.params + s.pset[gi];
+      auto process = [&](uint32_t c) {
+        const int64_t gj = g.nl_items[int64_t(c) * g.nl_ld + li];
+        const double* rp = s.gpos + 3 * gj;
+        process_pair(s, g, crash_mode, rebounce, gi, qx, qy, qz, Pi, gj, rp[0], rp[1], rp[2], acc);
+      };
+      if (__popc(hits) <= 2) {
+        // sums of <= 2 terms do not depend on the order
+        while (hits) {
+          process(uint32_t(__ffs(int(hits)) - 1));
+          hits &= hits - 1;
+        }
+      } else {
+        // >= 3: ascending j, like collide_kernel
+        int64_t last = -1;
+        while (hits) {
+          int64_t  best = INT64_MAX;
+          uint32_t bc   = 0;
+          for (uint32_t m = hits; m; m &= m - 1) {
+            const uint32_t c  = uint32_t(__ffs(int(m)) - 1);
+            const int64_t  gj = g.nl_items[int64_t(c) * g.nl_ld + li];
+            if (gj > last && gj < best) best = gj, bc = c;
+          }
+          if (best == INT64_MAX) break;
+          process(bc);
+          last = best;
+          hits &= ~(1u << bc);
+        }
+      }
+    }
+  }
+  store_result(s, li, acc);
+}
+
+// Are the lists still good for the positions of this pass?  One thread.
+__global__ void decide_kernel(NlCtl* c, double skin, int always, cudaGraphConditionalHandle handle, int has_handle) {
+  if (c->overflow) c->n_overflow_passes++;  // the previous pass fell back to collide_kernel
+  const uint32_t bits = c->disp_max_bits;  // largest squared displacement of the stepping launch since the last pass (float, rounded up)
+  c->disp_max_bits    = 0u;
+  const double d      = __dsqrt_ru(double(__uint_as_float(bits)));  // NaN stays NaN
+  double       D      = __dadd_ru(c->D_total, d);
+  const bool   rebuild = always || c->force || !c->valid || !(__dmul_ru(2.0, D) <= skin);
+  if (rebuild) {
+    D           = 0.0;
+    c->force    = 0u;
+    c->valid    = 1u;
+    c->overflow = 0u;
+    c->n_rebuilds++;
+  }
+  c->D_total = D;
+  c->rebuild = rebuild ? 1u : 0u;
+  c->n_passes++;
+  if (has_handle) cudaGraphSetConditional(handle, rebuild ? 1u : 0u);
 }
 
 }  // namespace
@@ -293,23 +429,52 @@ size_t collide_tmp_bytes(int64_t n_items) {
   return bytes;
 }
 
-int launch_collide(const DevState& s, const DevGrid& g, int crash_mode, double rebounce, void* cub_tmp, size_t cub_tmp_bytes, cudaStream_t stream) {
-  const int64_t n = s.n_global;
-  if (n <= 0) return 0;
+// table build: [box_reset, box,] count, scan, scatter.  Returns the number of own kernels.
+static int launch_table(const DevState& s, const DevGrid& g, void* cub_tmp, size_t cub_tmp_bytes, cudaStream_t stream) {
+  const int64_t  n      = s.n_global;
   const int      T      = 256;
   const unsigned nb     = unsigned((n + T - 1) / T);
   const int      filter = s.n_global > s.n;
   int            own    = 0;
-  cudaMemsetAsync(g.counters, 0, sizeof(unsigned long long), stream);
-  cudaMemsetAsync(g.count, 0, sizeof(uint32_t) * (size_t(g.n_buckets) + 2), stream);
+  cudaMemsetAsync(g.count, 0, sizeof(uint32_t) * (size_t(g.n_buckets) + 3), stream);
   if (filter) {
     box_reset_kernel<<<1, 32, 0, stream>>>(g.aabb);
     if (s.n > 0) box_kernel<<<unsigned(std::min<int64_t>((s.n + T - 1) / T, 296)), T, 0, stream>>>(s.gpos, s.shard_begin, s.n, g.aabb);
     own += 2;
   }
-  count_kernel<<<nb, T, 0, stream>>>(s.gpos, n, s.shard_begin, s.n, filter, g.aabb, g.n_buckets - 1, g.count, g.bucket, g.rank);
-  cub::DeviceScan::ExclusiveSum(cub_tmp, cub_tmp_bytes, g.count, g.begin, int(g.n_buckets) + 2, stream);
+  count_kernel<<<nb, T, 0, stream>>>(s.gpos, n, s.shard_begin, s.n, filter, g.aabb, g.n_buckets - 1, g.inv_cell, g.reach, g.count, g.bucket, g.rank);
+  cub::DeviceScan::ExclusiveSum(cub_tmp, cub_tmp_bytes, g.count, g.begin, int(g.n_buckets) + 3, stream);
   scatter_kernel<<<nb, T, 0, stream>>>(s.gpos, n, g.bucket, g.rank, g.begin, g.n_buckets, g.rec);
-  collide_kernel<<<unsigned((n + 127) / 128), 128, 0, stream>>>(s, g, crash_mode, rebounce);
-  return own + 3;  // own kernels: [box_reset, box,] count, scatter, collide (CUB's scan kernels and the memsets are not counted)
+  return own + 2;
+}
+
+// The full pass of every tick (sharded handles, or MRSB_NO_NEIGHBOUR_LISTS): table + collide_kernel.
+int launch_collide(const DevState& s, const DevGrid& g, int crash_mode, double rebounce, void* cub_tmp, size_t cub_tmp_bytes, cudaStream_t stream) {
+  const int64_t n = s.n_global;
+  if (n <= 0) return 0;
+  cudaMemsetAsync(g.counters, 0, sizeof(unsigned long long), stream);
+  const int own = launch_table(s, g, cub_tmp, cub_tmp_bytes, stream);
+  collide_kernel<<<unsigned((n + 127) / 128), 128, 0, stream>>>(s, g, crash_mode, rebounce, nullptr);
+  return own + 1;  // CUB's scan kernels and the memsets are not counted
+}
+
+// ---- the pass with neighbour lists, in three pieces so that api.cu can put the middle one into the
+// body of a conditional graph node -----------------------------------------------------------------
+int launch_collide_decide(const DevGrid& g, int always, cudaGraphConditionalHandle handle, int has_handle, cudaStream_t stream) {
+  cudaMemsetAsync(g.counters, 0, sizeof(unsigned long long), stream);
+  decide_kernel<<<1, 1, 0, stream>>>(g.ctl, g.skin, always, handle, has_handle);
+  return 1;
+}
+int launch_collide_rebuild(const DevState& s, const DevGrid& g, int crash_mode, double rebounce, void* cub_tmp, size_t cub_tmp_bytes, cudaStream_t stream) {
+  const int64_t n = s.n_global;
+  if (n <= 0) return 0;
+  const int own = launch_table(s, g, cub_tmp, cub_tmp_bytes, stream);
+  build_lists_kernel<<<unsigned((n + 127) / 128), 128, 0, stream>>>(s, g);
+  collide_kernel<<<unsigned((n + 127) / 128), 128, 0, stream>>>(s, g, crash_mode, rebounce, &g.ctl->overflow);
+  return own + 2;
+}
+int launch_collide_check(const DevState& s, const DevGrid& g, int crash_mode, double rebounce, cudaStream_t stream) {
+  if (s.n <= 0) return 0;
+  check_kernel<<<unsigned((s.n + 255) / 256), 256, 0, stream>>>(s, g, crash_mode, rebounce);
+  return 1;
 }

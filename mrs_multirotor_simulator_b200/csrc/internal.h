@@ -92,16 +92,40 @@ struct DevState {
   // into every peer's gather buffer over NVLink.  peers[r] = rank r's buffer (same parity as gpos).
   double* const* peers;  // device array [n_ranks], nullptr = exchange by NCCL all-gather instead
   int32_t  n_ranks, rank;
+  // neighbour lists of the collision pass: the stepping kernel atomicMax-es the float bits of the
+  // largest squared displacement |x_end - x_start|^2 of this launch here (nullptr = not tracked)
+  uint32_t* disp_max;
+};
+
+// neighbour lists (collide.cu): candidates per UAV kept between table rebuilds
+#define MRSB_NL_CAP 8
+struct NlCtl {
+  uint32_t disp_max_bits;  // written by the stepping kernel (DevState::disp_max points here)
+  uint32_t force;          // host: positions changed behind the stepping kernel's back -> rebuild
+  uint32_t valid;          // lists exist and no UAV overflowed its list
+  uint32_t overflow;       // the last rebuild found a UAV with more than MRSB_NL_CAP candidates
+  uint32_t rebuild;        // decision of the current pass
+  uint32_t pad_;
+  double   D_total;        // sum of the per-launch displacement bounds since the last rebuild
+  unsigned long long n_rebuilds, n_passes, n_overflow_passes;
 };
 
 // collision pass workspace
 struct DevGrid {
   uint32_t  n_buckets;  // power of two >= 2 * n_global
   uint32_t  bits;
+  double    inv_cell;   // 1 / cell edge
+  double    reach;      // cell / 2: the stencil covers [q - reach, q + reach)
+  double    list_r2;    // (sqrt(3) + skin)^2: who goes into a neighbour list
+  double    skin;       // lists are valid while 2 * D_total <= skin
+  uint32_t* nl_count;   // [nl_ld] candidates of each local UAV (nullptr: no lists, full pass every tick)
+  int32_t*  nl_items;   // [MRSB_NL_CAP][nl_ld] their global indices, slot-major
+  int64_t   nl_ld;
+  NlCtl*    ctl;
   uint32_t* bucket;     // [n_global] bucket of each UAV, 0xFFFFFFFF = not inserted (remote and outside this shard's box)
   uint32_t* rank;       // [n_global] arrival rank inside its bucket
-  uint32_t* count;      // [n_buckets+2] occupancy histogram; [n_buckets] mirrors bucket 0, last entry stays 0
-  uint32_t* begin;      // [n_buckets+2] exclusive scan of count; begin[n_buckets] = number of inserted UAVs
+  uint32_t* count;      // [n_buckets+3] occupancy histogram; [n_buckets], [n_buckets+1] mirror buckets 0 and 1, last entry stays 0
+  uint32_t* begin;      // [n_buckets+3] exclusive scan of count; begin[n_buckets] = number of inserted UAVs
   double4*  rec;        // [2*n_global] records {x,y,z, index bits} grouped by bucket (+ the mirror copies of bucket 0)
   unsigned long long* aabb;  // [6] order-preserving encoding of min xyz / max xyz of this shard's positions
   int32_t*  pairs;      // [pair_cap][2]
@@ -114,11 +138,16 @@ struct DevGrid {
 int launch_step(const DevState& s, const DevParams* uniform_params, double dt, int k_substeps, int uniform_mode, int uniform_nm, bool any_moment,
                 cudaStream_t stream);
 int launch_collide(const DevState& s, const DevGrid& g, int crash_mode, double rebounce, void* cub_tmp, size_t cub_tmp_bytes, cudaStream_t stream);
+// the pass with neighbour lists: decide (always) | rebuild (body of the graph's conditional node) | check (always)
+int launch_collide_decide(const DevGrid& g, int always, cudaGraphConditionalHandle handle, int has_handle, cudaStream_t stream);
+int launch_collide_rebuild(const DevState& s, const DevGrid& g, int crash_mode, double rebounce, void* cub_tmp, size_t cub_tmp_bytes, cudaStream_t stream);
+int launch_collide_check(const DevState& s, const DevGrid& g, int crash_mode, double rebounce, cudaStream_t stream);
 size_t collide_tmp_bytes(int64_t n_global);
 int launch_publish_positions(const DevState& s, cudaStream_t stream);
 // cross-GPU hand-shake of the fused exchange: tell every peer "my positions of `epoch` have landed", wait for theirs
-int launch_p2p_signal(unsigned long long* const* peer_flags, int n_ranks, int rank, unsigned long long epoch, cudaStream_t stream);
-int launch_p2p_wait(const unsigned long long* flags, int n_ranks, int rank, unsigned long long epoch, int* status, cudaStream_t stream);
+// `disp` (may be nullptr): this rank's displacement word — sent along with the epoch, and raised to the largest of all ranks' by the wait
+int launch_p2p_signal(unsigned long long* const* peer_flags, int n_ranks, int rank, unsigned long long epoch, const uint32_t* disp, cudaStream_t stream);
+int launch_p2p_wait(const unsigned long long* flags, int n_ranks, int rank, unsigned long long epoch, int* status, uint32_t* disp, cudaStream_t stream);
 
 int launch_scatter_input(const DevState& s, int mode, int64_t n, const int32_t* idx_dev, const double* payload_dev, int stride, cudaStream_t stream);
 // payload[k][0..rows) <-> rows [row0, row0+rows) of a tiled array with `rows_total` components

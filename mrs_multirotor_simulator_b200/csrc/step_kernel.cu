@@ -38,38 +38,52 @@ __global__ void publish_positions_kernel(DevState s) {
   gp[2]      = s.st[tix(ST_ROWS, 2, i)];
 }
 
-__global__ void p2p_signal_kernel(unsigned long long* const* peer_flags, int n_ranks, int rank, unsigned long long epoch) {
-  __threadfence_system();
+// Flag block of a rank: [0, G) epochs written by the peers; [G, 3G) the peers' displacement words
+// (float bits of the largest squared displacement of their stepping launch), double-buffered by epoch
+// parity — a peer is at most one tick ahead, so the slot of epoch e is not overwritten before e + 2.
+__global__ void p2p_signal_kernel(unsigned long long* const* peer_flags, int n_ranks, int rank, unsigned long long epoch, const uint32_t* disp) {
   const int r = threadIdx.x;
+  if (disp && r < n_ranks && r != rank)
+    *reinterpret_cast<volatile unsigned long long*>(peer_flags[r] + n_ranks + 2 * rank + int(epoch & 1ull)) = (unsigned long long)*disp;
+  __threadfence_system();
   if (r < n_ranks && r != rank) *reinterpret_cast<volatile unsigned long long*>(peer_flags[r] + rank) = epoch;
 }
 // one lane per peer spins (bounded) on this rank's own flag slots, which the peers write over NVLink
-__global__ void p2p_wait_kernel(const unsigned long long* flags, int n_ranks, int rank, unsigned long long epoch, int* status, long long budget) {
+__global__ void p2p_wait_kernel(const unsigned long long* flags, int n_ranks, int rank, unsigned long long epoch, int* status, long long budget,
+                                uint32_t* disp) {
   const int r = threadIdx.x;
   if (r < n_ranks && r != rank) {
     const long long t0 = clock64();
+    bool            ok = true;
     while (*reinterpret_cast<const volatile unsigned long long*>(flags + r) < epoch) {
       if (clock64() - t0 > budget) {  // a peer is gone; report instead of hanging the GPU
         *status = 1;
+        ok      = false;
         break;
       }
       __nanosleep(64);
+    }
+    if (disp) {
+      // the swarm-wide displacement bound: the largest of every rank's (a lost peer counts as "unbounded")
+      __threadfence_system();
+      const uint32_t theirs = ok ? uint32_t(*reinterpret_cast<const volatile unsigned long long*>(flags + n_ranks + 2 * r + int(epoch & 1ull))) : 0xFFFFFFFFu;
+      atomicMax(disp, theirs);
     }
   }
 }
 }  // namespace
 
-int launch_p2p_signal(unsigned long long* const* peer_flags, int n_ranks, int rank, unsigned long long epoch, cudaStream_t stream) {
-  p2p_signal_kernel<<<1, 32, 0, stream>>>(peer_flags, n_ranks, rank, epoch);
+int launch_p2p_signal(unsigned long long* const* peer_flags, int n_ranks, int rank, unsigned long long epoch, const uint32_t* disp, cudaStream_t stream) {
+  p2p_signal_kernel<<<1, 32, 0, stream>>>(peer_flags, n_ranks, rank, epoch, disp);
   return 1;
 }
-int launch_p2p_wait(const unsigned long long* flags, int n_ranks, int rank, unsigned long long epoch, int* status, cudaStream_t stream) {
+int launch_p2p_wait(const unsigned long long* flags, int n_ranks, int rank, unsigned long long epoch, int* status, uint32_t* disp, cudaStream_t stream) {
   static long long budget = 0;
   if (!budget) {
     const char* e = getenv("MRSB_P2P_TIMEOUT_MS");
     budget        = (e ? atoll(e) : 20000LL) * 2000000LL;  // default 20 s at ~2 GHz SM clock
   }
-  p2p_wait_kernel<<<1, 32, 0, stream>>>(flags, n_ranks, rank, epoch, status, budget);
+  p2p_wait_kernel<<<1, 32, 0, stream>>>(flags, n_ranks, rank, epoch, status, budget, disp);
   return 1;
 }
 

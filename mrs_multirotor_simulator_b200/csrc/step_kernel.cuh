@@ -346,7 +346,7 @@ struct TileIn {
 // per thread after the last read through `in` (the staged kernel re-arms its TMA there).
 template <int NM_T, int MODE_T, bool ONE, class Hook>
 DEV void step_uav(const DevState& s, const TileIn& in, const int64_t tile, const uint32_t flags0, const DevParams* batch_params, const int32_t pset,
-                  const double dt, const int k_sub_arg, const int any_moment, double* xyz_stage, Hook after_loads) {
+                  const double dt, const int k_sub_arg, const int any_moment, double* xyz_stage, uint32_t& disp_bits, Hook after_loads) {
   // batch_params: the whole batch's single parameter set in the constant bank (staged kernel), or
   // nullptr -> this UAV's entry of the table in HBM (read-only path)
   const DevParams* __restrict__ P = batch_params ? batch_params : s.params + pset;
@@ -381,6 +381,7 @@ DEV void step_uav(const DevState& s, const TileIn& in, const int64_t tile, const
 
   // ---- load state -------------------------------------------------------------------------
   Vec3 x = mk(LD(t_st, 0), LD(t_st, 1), LD(t_st, 2));
+  const Vec3 x_start = x;  // for the displacement bound of the collision pass' neighbour lists
   Vec3 v = mk(LD(t_st, 3), LD(t_st, 4), LD(t_st, 5));
   Rot  R;
   R.c0   = mk(LD(t_st, 6), LD(t_st, 7), LD(t_st, 8));
@@ -751,6 +752,9 @@ DEV void step_uav(const DevState& s, const TileIn& in, const int64_t tile, const
   ST(o_imu, 2, imu.z);
   const uint32_t new_flags = flags & ~FLAG_VPREV;
   if (valid) {
+    // squared displacement of this launch as float bits, rounded up (NaN keeps the largest pattern)
+    const double ddx = x.x - x_start.x, ddy = x.y - x_start.y, ddz = x.z - x_start.z;
+    disp_bits = max(disp_bits, __float_as_uint(fabsf(__double2float_ru(fma(ddx, ddx, fma(ddy, ddy, ddz * ddz))))));
     if (new_flags != flags0) s.flags[i] = new_flags;
     // packed position for the collision pass / the cross-shard all-gather
     const int64_t go = 3 * (s.shard_begin + i);
@@ -781,6 +785,14 @@ DEV void step_uav(const DevState& s, const TileIn& in, const int64_t tile, const
 #undef ST
 }
 
+// Largest squared displacement of the launch (float bits) -> DevState::disp_max: one atomic per warp
+// at most, and none once the word already holds a value at least as large.
+DEV void report_displacement(const DevState& s, uint32_t disp_bits) {
+  if (!s.disp_max) return;
+  disp_bits = __reduce_max_sync(0xffffffffu, disp_bits);
+  if ((threadIdx.x & 31) == 0 && disp_bits > *reinterpret_cast<volatile uint32_t*>(s.disp_max)) atomicMax(s.disp_max, disp_bits);
+}
+
 // ---- direct kernel: one CTA per tile, inputs read straight from HBM ----------------------------
 template <int NM_T, int MODE_T, bool ONE>
 __global__ void __launch_bounds__(MRSB_STEP_THREADS, MRSB_STEP_MINB(ONE, MODE_T)) uav_step_kernel(DevState s, double dt, int k_sub, int any_moment) {
@@ -792,7 +804,9 @@ __global__ void __launch_bounds__(MRSB_STEP_THREADS, MRSB_STEP_MINB(ONE, MODE_T)
   in.cmd  = s.cmd + (tile * CMD_ROWS) * MRSB_TILE + threadIdx.x;
   in.fext = s.fext + (tile * F3_ROWS) * MRSB_TILE + threadIdx.x;
   const int64_t i = min(tile * MRSB_TILE + threadIdx.x, s.n - 1);
-  step_uav<NM_T, MODE_T, ONE>(s, in, tile, s.flags[i], nullptr, s.pset[s.shard_begin + i], dt, k_sub, any_moment, nullptr, [] {});
+  uint32_t disp_bits = 0u;
+  step_uav<NM_T, MODE_T, ONE>(s, in, tile, s.flags[i], nullptr, s.pset[s.shard_begin + i], dt, k_sub, any_moment, nullptr, disp_bits, [] {});
+  report_displacement(s, disp_bits);
 }
 
 // ---- staged kernel: persistent CTAs, the NEXT tile's inputs are fetched by the TMA unit into
@@ -852,6 +866,7 @@ __global__ void __launch_bounds__(MRSB_STEP_THREADS, MRSB_STEP_MINB(ONE, MODE_T)
   // the per-UAV word that is not part of the tile image is prefetched one tile ahead
   int64_t  i0        = min(tile * MRSB_TILE + threadIdx.x, s.n - 1);
   uint32_t flags_cur = tile < n_tiles ? s.flags[i0] : 0u;
+  uint32_t disp_bits = 0u;
   for (; tile < n_tiles; tile += gridDim.x) {
     const int64_t next = tile + gridDim.x;
     uint32_t      flags_next = 0u;
@@ -860,7 +875,7 @@ __global__ void __launch_bounds__(MRSB_STEP_THREADS, MRSB_STEP_MINB(ONE, MODE_T)
     double*    stage = (BULK && full) ? xyz_out + out_slot * (3 * MRSB_TILE) : nullptr;
     mbar_wait(&bar, phase);
     phase ^= 1u;
-    step_uav<NM_T, MODE_T, ONE>(s, in, tile, flags_cur, &params, 0, dt, k_sub, any_moment, stage, [&] {
+    step_uav<NM_T, MODE_T, ONE>(s, in, tile, flags_cur, &params, 0, dt, k_sub, any_moment, stage, disp_bits, [&] {
       if (BULK && threadIdx.x == 0) tma_store_wait_read<1>();  // the staging buffer about to be refilled has been read out
       __syncthreads();  // every lane has its inputs in registers: the image may be overwritten
       if (threadIdx.x == 0 && next < n_tiles) stage_tile<NM_T, MODE_T>(s, sm, &bar, next);
@@ -884,6 +899,7 @@ __global__ void __launch_bounds__(MRSB_STEP_THREADS, MRSB_STEP_MINB(ONE, MODE_T)
     flags_cur = flags_next;
   }
   if (BULK && threadIdx.x == 0) tma_store_wait_all();
+  report_displacement(s, disp_bits);
 }
 
 // CTAs of the staged kernel that fit on the device (persistent grid), cached per instantiation
