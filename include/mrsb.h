@@ -334,6 +334,11 @@ typedef struct mrsb_device_view {
   uint8_t*  input_mode;
 } mrsb_device_view;
 int mrsb_get_device_view(mrsb_handle h, mrsb_device_view* out);
+/* After writing through the view: positions (state rows 0-2) -> mrsb_publish_positions, so that the
+ * collision pass sees them; ext_force -> mrsb_forces_written, so that the next collision pass replaces
+ * every UAV's force as MultirotorSimulator::handleCollisions does (SIM:356-358) and not only the ones it
+ * last wrote itself.  mrsb_apply_force does this on its own. */
+int mrsb_forces_written(mrsb_handle h);
 
 /* ---- roofline denominators, measured on `device` (used by bench.py) --------------------------
  * FP64 FMA throughput in TFLOP/s (2 flop per FMA) and device-to-device copy bandwidth in GB/s

@@ -208,6 +208,10 @@ class UavBatch:
         f = np.ascontiguousarray(f, dtype=np.float64).reshape(n, 3)
         check(self._L.mrsb_apply_force(self.h, n, _ptr(idx), _ptr(f)))
 
+    def forces_written(self):
+        """Call after writing ext_force through device_view(): the next collision pass then replaces every UAV's force."""
+        check(self._L.mrsb_forces_written(self.h))
+
     def get_force(self, idx=None):
         idx = _idx(idx)
         out = np.empty((self._n(idx), 3))

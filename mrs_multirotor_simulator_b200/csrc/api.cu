@@ -155,6 +155,7 @@ struct mrsb_sim {
   int      steps_since_pass    = 0;     // stepping launches since the last collision pass
   bool     positions_touched   = true;  // positions were written by something else than ONE stepping launch
   int      rebuild_own         = 0;     // own kernels of one rebuild (for the launch counter)
+  int64_t  list_passes         = 0;     // passes that went through decide_kernel (it counts them too: NlCtl::n_passes)
   int64_t  rebuilds_counted    = 0;
   uint32_t* h_one              = nullptr;  // pinned constant 1 (source of the async "force rebuild" copy)
 
@@ -911,6 +912,7 @@ static int collide_local(mrsb_sim* h) {
       CU(cudaMemcpyAsync(&h->grid.ctl->force, h->h_one, sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
     h->positions_touched = false;
     h->steps_since_pass  = 0;
+    h->list_passes++;
     if (!h->coll_graph[k] && !getenv("MRSB_NO_GRAPH")) h->coll_graph[k] = build_list_graph(h, &h->coll_graph_own[k], &h->rebuild_own);
     if (h->coll_graph[k]) {
       CU(cudaGraphLaunch(h->coll_graph[k], h->stream));
@@ -1127,8 +1129,25 @@ int mrsb_has_crashed(mrsb_handle h, int64_t n, const int32_t* idx, int32_t* cras
   return MRSB_OK;
 }
 
+// forces were written by something else than the collision pass: the next pass must replace every UAV's
+// force (SIM:356-358), not only the ones it knows to be non-zero
+static int forces_written(mrsb_sim* h) {
+  if (!h->grid.ctl) return MRSB_OK;
+  const unsigned long long until = (unsigned long long)h->list_passes + 1ull;  // index of the next pass that goes through decide_kernel
+  CU(cudaMemcpyAsync(&h->grid.ctl->write_all_until, &until, sizeof(until), cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));  // `until` lives on this stack frame
+  return MRSB_OK;
+}
+
+int mrsb_forces_written(mrsb_handle h) {
+  GUARD(h);
+  return forces_written(h);
+}
+
 int mrsb_apply_force(mrsb_handle h, int64_t n, const int32_t* idx, const double* force) {
   GUARD(h);
+  int rc = forces_written(h);
+  if (rc) return rc;
   return put_rows(h, h->ds.fext, F3_ROWS, 0, 3, n, idx, force, 3, 0);
 }
 int mrsb_get_external_force(mrsb_handle h, int64_t n, const int32_t* idx, double* force) {

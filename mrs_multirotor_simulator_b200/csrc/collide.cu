@@ -41,7 +41,12 @@
 // same bits either way: the lists only choose which pairs are tested.  Anything that moves UAVs
 // other than one stepping launch (set_state, publish_positions, several launches between passes)
 // forces a rebuild; a UAV with more than NL_CAP candidates switches the pass back to the full
-// `collide_kernel` until the crowd dissolves.  Sharded handles always run the full pass.
+// `collide_kernel` until the crowd dissolves.  Sharded handles use the lists when the fused exchange
+// carries every rank's displacement bound (api.cu), the full pass otherwise.
+// Bit 31 of a UAV's list-count word says "its external force may be non-zero": a pass must REPLACE every
+// UAV's force (SIM:356-358), but writing 24 zero bytes over 24 zero bytes for the (vast) majority without a
+// neighbour is most of a list-only pass — a UAV with an empty list and a clear bit is left alone.  Whoever
+// writes forces elsewhere (mrsb_apply_force, mrsb_forces_written) makes the next pass write them all.
 //
 // Crash mode (SIM:347-348) marks the NEIGHBOUR crashed.  A shard must not write remote state, so the
 // owner of i evaluates the mirrored test d2 < ((arm_j+prop_j)+arm_i)+prop_i — the exact threshold
@@ -224,11 +229,15 @@ DEV void process_pair(const DevState& s, const DevGrid& g, int crash_mode, doubl
 }
 
 // SIM:356-358: forces replace external_force_ for the next tick (zero in crash mode, SIM:315-319)
+#define NL_LIVE 0x80000000u  // bit 31 of nl_count[]: the UAV's external force may be non-zero
 DEV void store_result(const DevState& s, int64_t li, const PairAcc& acc) {
   s.fext[tix(F3_ROWS, 0, li)] = acc.fx;
   s.fext[tix(F3_ROWS, 1, li)] = acc.fy;
   s.fext[tix(F3_ROWS, 2, li)] = acc.fz;
   if (acc.crashed_me) s.flags[li] |= FLAG_CRASHED;
+}
+DEV bool nonzero(const PairAcc& acc) {
+  return !(acc.fx == 0.0 && acc.fy == 0.0 && acc.fz == 0.0);  // NaN counts as non-zero
 }
 
 #ifndef MRSB_COLLIDE_MINB
@@ -309,6 +318,7 @@ __global__ void __launch_bounds__(128, MRSB_COLLIDE_MINB) collide_kernel(DevStat
     }
   }
   store_result(s, li, acc);
+  if (g.nl_count) g.nl_count[li] = (g.nl_count[li] & ~NL_LIVE) | (nonzero(acc) ? NL_LIVE : 0u);
 }
 
 // ---- neighbour lists ---------------------------------------------------------------------------
@@ -342,7 +352,7 @@ __global__ void __launch_bounds__(128, MRSB_COLLIDE_MINB) build_lists_kernel(Dev
       for (uint32_t t = st.lo[k] + 1; t < st.hi[k]; t++) take(g.rec[t], k);
     }
   }
-  g.nl_count[li] = min(cnt, uint32_t(MRSB_NL_CAP));
+  g.nl_count[li] = min(cnt, uint32_t(MRSB_NL_CAP)) | (g.nl_count[li] & NL_LIVE);
   if (cnt > MRSB_NL_CAP) {  // too crowded for the lists: this pass and the next ones run the full kernel
     g.ctl->overflow = 1u;
     g.ctl->valid    = 0u;
@@ -350,20 +360,37 @@ __global__ void __launch_bounds__(128, MRSB_COLLIDE_MINB) build_lists_kernel(Dev
 }
 
 // One thread per UAV: the exact predicate on the CURRENT positions of the listed candidates.
+// (Tried and dropped: remembering each candidate's distance at build time and skipping the fetch while
+// d_build - 2 D is still above sqrt(3) — the extra dependent load cost more than the skipped gathers.)
 __global__ void __launch_bounds__(256) check_kernel(DevState s, DevGrid g, int crash_mode, double rebounce) {
   if (g.ctl->overflow) return;  // collide_kernel did this pass
   const int64_t li = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (li >= s.n) return;
-  const uint32_t cnt = g.nl_count[li];
-  PairAcc        acc;
+  const uint32_t word = g.nl_count[li];
+  const uint32_t cnt  = word & ~NL_LIVE;
+  // forces were written from outside since the last pass (this pass' index <= write_all_until): replace them all
+  const bool     live = (word & NL_LIVE) || g.ctl->n_passes <= g.ctl->write_all_until;
+  if (cnt == 0u && !live) return;  // no candidate, force already zero
+  PairAcc acc;
   if (cnt) {
     const int64_t gi = li + s.shard_begin;
     const double* qp = s.gpos + 3 * gi;
     const double  qx = qp[0], qy = qp[1], qz = qp[2];
     uint32_t      hits = 0;
-    for (uint32_t c = 0; c < cnt; c++) {
-      const double* rp = s.gpos + 3 * int64_t(g.nl_items[int64_t(c) * g.nl_ld + li]);
-      if (nf_dist2(qx, qy, qz, rp[0], rp[1], rp[2]) < 3.0) hits |= 1u << c;  // NF:305-309
+    for (uint32_t base = 0; base < cnt; base += 4) {
+      // four candidates at a time: indices, then positions, then distances (independent loads in flight)
+      int32_t gj[4];
+      double  r[4][3];
+#pragma unroll
+      for (int u = 0; u < 4; u++) gj[u] = base + u < cnt ? g.nl_items[int64_t(base + u) * g.nl_ld + li] : -1;
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const double* rp = s.gpos + 3 * int64_t(max(gj[u], 0));
+        r[u][0] = rp[0], r[u][1] = rp[1], r[u][2] = rp[2];
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+        if (gj[u] >= 0 && nf_dist2(qx, qy, qz, r[u][0], r[u][1], r[u][2]) < 3.0) hits |= 1u << (base + u);  // NF:305-309
     }
     if (hits) {
       const DevParams* __restrict__ Pi = s.params + s.pset[gi];
@@ -397,11 +424,15 @@ __global__ void __launch_bounds__(256) check_kernel(DevState s, DevGrid g, int c
       }
     }
   }
-  store_result(s, li, acc);
+  const bool nz = nonzero(acc);
+  if (live || nz) store_result(s, li, acc);
+  else if (acc.crashed_me) s.flags[li] |= FLAG_CRASHED;
+  if (nz != bool(word & NL_LIVE)) g.nl_count[li] = cnt | (nz ? NL_LIVE : 0u);
 }
 
 // Are the lists still good for the positions of this pass?  One thread.
-__global__ void decide_kernel(NlCtl* c, double skin, int always, cudaGraphConditionalHandle handle, int has_handle) {
+__global__ void decide_kernel(NlCtl* c, unsigned long long* pair_counter, double skin, int always, cudaGraphConditionalHandle handle, int has_handle) {
+  *pair_counter = 0ull;  // pairs found by this pass
   if (c->overflow) c->n_overflow_passes++;  // the previous pass fell back to collide_kernel
   const uint32_t bits = c->disp_max_bits;  // largest squared displacement of the stepping launch since the last pass (float, rounded up)
   c->disp_max_bits    = 0u;
@@ -461,8 +492,7 @@ int launch_collide(const DevState& s, const DevGrid& g, int crash_mode, double r
 // ---- the pass with neighbour lists, in three pieces so that api.cu can put the middle one into the
 // body of a conditional graph node -----------------------------------------------------------------
 int launch_collide_decide(const DevGrid& g, int always, cudaGraphConditionalHandle handle, int has_handle, cudaStream_t stream) {
-  cudaMemsetAsync(g.counters, 0, sizeof(unsigned long long), stream);
-  decide_kernel<<<1, 1, 0, stream>>>(g.ctl, g.skin, always, handle, has_handle);
+  decide_kernel<<<1, 1, 0, stream>>>(g.ctl, g.counters, g.skin, always, handle, has_handle);
   return 1;
 }
 int launch_collide_rebuild(const DevState& s, const DevGrid& g, int crash_mode, double rebounce, void* cub_tmp, size_t cub_tmp_bytes, cudaStream_t stream) {

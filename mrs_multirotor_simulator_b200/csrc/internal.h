@@ -108,6 +108,7 @@ struct NlCtl {
   uint32_t pad_;
   double   D_total;        // sum of the per-launch displacement bounds since the last rebuild
   unsigned long long n_rebuilds, n_passes, n_overflow_passes;
+  unsigned long long write_all_until;  // host: passes up to this index must write every UAV's force (they were written from outside)
 };
 
 // collision pass workspace
@@ -118,7 +119,7 @@ struct DevGrid {
   double    reach;      // cell / 2: the stencil covers [q - reach, q + reach)
   double    list_r2;    // (sqrt(3) + skin)^2: who goes into a neighbour list
   double    skin;       // lists are valid while 2 * D_total <= skin
-  uint32_t* nl_count;   // [nl_ld] candidates of each local UAV (nullptr: no lists, full pass every tick)
+  uint32_t* nl_count;   // [nl_ld] candidates of each local UAV; bit 31: its external force may be non-zero (nullptr: no lists)
   int32_t*  nl_items;   // [MRSB_NL_CAP][nl_ld] their global indices, slot-major
   int64_t   nl_ld;
   NlCtl*    ctl;

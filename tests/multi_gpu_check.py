@@ -29,13 +29,15 @@ def log(*a):
         print(f"[r{os.environ['RANK']}]", *a, flush=True)
 
 
-def run(world, rank, local, crash, ticks=60, n=12001):
+def run(world, rank, local, crash, ticks=60, n=12001, area=90.0, every=10):
+    """area 90 m: a crowd (every neighbour list overflows -> full kernel every tick); area 700 m: a sparse
+    swarm whose neighbour lists live for many ticks and contain UAVs of other shards."""
     ticks = int(os.environ.get("MGC_TICKS", ticks))
     n = int(os.environ.get("MGC_N", n))
     log("run crash", crash, "no_p2p", os.environ.get("MRSB_NO_P2P"))
     types = [airframe("x500", ground_enabled=True), airframe("f550", ground_enabled=True), airframe("naki", ground_enabled=True)]
     tou = (np.arange(n) * 7 % 3).astype(np.int32)
-    xyz = np.stack([rand(21, 0, n, 0, 90), rand(21, 1, n, 0, 90), rand(21, 2, n, 1, 7)], axis=1)  # well mixed: shards overlap everywhere
+    xyz = np.stack([rand(21, 0, n, 0, area), rand(21, 1, n, 0, area), rand(21, 2, n, 1, 7)], axis=1)  # well mixed: shards overlap everywhere
     cmd = np.stack([rand(22, 1, n, -2, 2), rand(22, 2, n, -2, 2), rand(22, 3, n, -0.5, 0.5), rand(22, 4, n, -1, 1)], axis=1)
     begin, count = shard_range(n, world, rank)
     mine = UavBatch(types, type_of_uav=tou, spawn_xyz=xyz[begin:begin + count], n=count, device=local, n_global=n, shard_begin=begin)
@@ -57,7 +59,7 @@ def run(world, rank, local, crash, ticks=60, n=12001):
         if rank == 0:
             whole.make_step(0.01)
             whole.handle_collisions()
-        if t % 10 == 9:
+        if t % every == every - 1:
             p = mine.get_collision_pairs()
             log("tick", t, "pairs", len(p))
             gathered = [None] * world
@@ -83,7 +85,11 @@ def run(world, rank, local, crash, ticks=60, n=12001):
             assert np.array_equal(ref[k], got), f"{k} differs from the unsharded run"
         assert n_pairs > 0
     mode = mine.exchange_mode()
-    log("run ok")
+    info = mine.collision_info()
+    assert info["neighbour_lists"] == (mode == 2), info  # lists need the displacement bound of every rank: carried by the peer hand-shake only
+    if mode == 2 and area > 500:
+        assert 0 < info["rebuilds"] < info["passes"] // 3 and info["overflow_passes"] == 0, info  # the lists were really used between rebuilds
+    log("run ok", info)
     dist.barrier()
     mine.close()
     if whole is not None:
@@ -104,6 +110,7 @@ def main():
             os.environ.pop("MRSB_NO_P2P", None)
         for crash in (False, True):
             results.append(run(world, rank, local, crash))
+        results.append(run(world, rank, local, False, ticks=400, area=700.0, every=25))
     dist.barrier()
     if rank == 0:
         print("MULTI_GPU_OK world=%d exchange_modes=%s pairs=%s" % (world, [m for m, _ in results], [p for _, p in results]), flush=True)

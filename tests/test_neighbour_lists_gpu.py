@@ -167,3 +167,33 @@ def test_applied_forces_are_replaced_by_the_next_pass():
     b.make_step(0.01)
     b.handle_collisions()
     assert not b.get_force().any()
+
+
+def test_forces_written_through_the_device_view_are_replaced_after_forces_written():
+    """ext_force written behind the library's back (RL loop through mrsb_get_device_view): after
+    mrsb_forces_written the next pass replaces every force; a colliding pair keeps getting its force."""
+    n = 256
+    spawn = grid_spawn(n, pitch=8.0, z=5.0)
+    spawn[1] = spawn[0] + np.array([0.3, 0.0, 0.0])  # one colliding pair
+    b = batch([af("x500")], np.zeros(n, dtype=np.int32), spawn)
+    b.set_collisions(True, False, 100.0)
+    for _ in range(3):
+        b.make_step(0.01)
+        b.handle_collisions()
+    f0 = b.get_force()
+    assert f0[0].any() and f0[1].any() and not f0[2:].any()
+    # overwrite every force on the device, tell the library, step once
+    from cuda.bindings import runtime as cudart
+
+    v = b.device_view()
+    ones = np.ones(((n + v.tile - 1) // v.tile) * 3 * v.tile)
+    b.sync()
+    (err,) = cudart.cudaMemcpy(v.ext_force, ones.ctypes.data, ones.nbytes, cudart.cudaMemcpyKind.cudaMemcpyHostToDevice)
+    assert int(err) == 0
+    assert np.all(b.get_force() == 1.0)
+    b.forces_written()
+    b.make_step(0.01)
+    b.handle_collisions()
+    f1 = b.get_force()
+    assert f1[0].any() and f1[1].any() and not f1[2:].any()
+    assert not np.any(f1 == 1.0)

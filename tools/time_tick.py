@@ -44,4 +44,7 @@ for a, e in ev:
     e.record(st)
 torch.cuda.synchronize()
 out["step_us"] = float(np.median([a.elapsed_time(e) for a, e in ev])) * 1000
-print(json.dumps(out))
+out["collision_us_avg"] = out["second"]["tick_us"] - out["step_us"]
+print(json.dumps({k: out[k] for k in ("step_us", "collision_us_avg", "first", "second", "lists", "cell_env")}))
+if os.environ.get("VERBOSE"):
+    print(json.dumps(out))
