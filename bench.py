@@ -183,7 +183,7 @@ def collision_report(tick_ms, step_ms, rebuild_ms, info0, info1):
            "neighbour_lists": info1["neighbour_lists"], "ms_rebuild_pass_alone": rebuild_ms}
     if info1["neighbour_lists"]:
         out.update({"list_radius_m": info1["list_radius"], "skin_m": info1["skin"], "rebuild_fraction": (info1["rebuilds"] - info0["rebuilds"]) / passes,
-                    "overflow_fallback_fraction": (info1["overflow_passes"] - info0["overflow_passes"]) / passes})
+                    "crowded_uavs_at_last_rebuild": info1["crowded_uavs"]})
     return out
 
 

@@ -291,8 +291,8 @@ int mrsb_get_counters(mrsb_handle h, int64_t* out5);
 /* How the collision pass (SIM:295-359) is organised on this handle: [0] cell edge of the spatial hash in
  * metres, [1] 1 if neighbour lists are kept between table rebuilds (single-shard handles), [2] list
  * radius, [3] skin (the lists survive while twice the accumulated displacement bound stays below it),
- * [4] passes decided on the device, [5] of which rebuilt the table, [6] passes that fell back to the
- * full kernel because a UAV had more candidates than a list holds, [7] buckets of the table.
+ * [4] passes decided on the device, [5] of which rebuilt the table, [6] UAVs that had more candidates
+ * than a list holds at the last rebuild (they walk the table's stencil instead), [7] buckets of the table.
  * Diagnostics only: pair lists, forces and crash flags do not depend on any of it. */
 int mrsb_get_collision_info(mrsb_handle h, double* out8);
 

@@ -326,7 +326,7 @@ class UavBatch:
         out = np.zeros(8, dtype=np.float64)
         check(self._L.mrsb_get_collision_info(self.h, _ptr(out)))
         return dict(cell=float(out[0]), neighbour_lists=bool(out[1]), list_radius=float(out[2]), skin=float(out[3]), passes=int(out[4]),
-                    rebuilds=int(out[5]), overflow_passes=int(out[6]), n_buckets=int(out[7]))
+                    rebuilds=int(out[5]), crowded_uavs=int(out[6]), n_buckets=int(out[7]))
 
     # ---- sharded operation ----------------------------------------------------------------------
     @staticmethod

@@ -888,7 +888,7 @@ static cudaGraphExec_t build_list_graph(mrsb_sim* h, int* own_fixed, int* own_re
     cudaGraph_t body = cp.conditional.phGraph_out[0];
     if (cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking) != cudaSuccess) break;
     if (cudaStreamBeginCaptureToGraph(side, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal) != cudaSuccess) break;
-    *own_rebuild = launch_collide_rebuild(h->ds, h->grid, h->coll_crash, h->coll_rebounce, h->cub_tmp, h->cub_tmp_bytes, side);
+    *own_rebuild = launch_collide_rebuild(h->ds, h->grid, h->cub_tmp, h->cub_tmp_bytes, side);
     cudaGraph_t body_out = nullptr;
     if (cudaStreamEndCapture(side, &body_out) != cudaSuccess) break;
     if (cudaStreamUpdateCaptureDependencies(h->stream, &cond, 1, cudaStreamSetCaptureDependencies) != cudaSuccess) break;
@@ -920,7 +920,7 @@ static int collide_local(mrsb_sim* h) {
     } else {
       // no graph (MRSB_NO_GRAPH, or conditional nodes unavailable): rebuild every pass
       h->n_launches += launch_collide_decide(h->grid, 1, cudaGraphConditionalHandle{}, 0, h->stream);
-      h->rebuild_own = launch_collide_rebuild(h->ds, h->grid, h->coll_crash, h->coll_rebounce, h->cub_tmp, h->cub_tmp_bytes, h->stream);
+      h->rebuild_own = launch_collide_rebuild(h->ds, h->grid, h->cub_tmp, h->cub_tmp_bytes, h->stream);
       h->n_launches += launch_collide_check(h->ds, h->grid, h->coll_crash, h->coll_rebounce, h->stream);
     }
     h->n_passes++;
@@ -1437,7 +1437,7 @@ int mrsb_get_collision_info(mrsb_handle h, double* out8) {
   out8[3] = h->lists_on ? h->grid.skin : 0.0;
   out8[4] = double(ctl.n_passes);
   out8[5] = double(ctl.n_rebuilds);
-  out8[6] = double(ctl.n_overflow_passes);
+  out8[6] = double(ctl.n_crowded);
   out8[7] = double(h->grid.n_buckets);
   return MRSB_OK;
 }

@@ -40,8 +40,10 @@
 // condition `decide_kernel` sets on the device, so no host round trip is involved.  Results are the
 // same bits either way: the lists only choose which pairs are tested.  Anything that moves UAVs
 // other than one stepping launch (set_state, publish_positions, several launches between passes)
-// forces a rebuild; a UAV with more than NL_CAP candidates switches the pass back to the full
-// `collide_kernel` until the crowd dissolves.  Sharded handles use the lists when the fused exchange
+// forces a rebuild.  A UAV with more than NL_CAP candidates keeps no list: it remembers where its
+// record sits in the (now ageing) table and, every pass, walks the stencil of its build-time cell —
+// the records there are a superset of its possible neighbours for as long as the lists are valid —
+// testing each candidate's CURRENT position (`check_crowded`).  Only the crowded UAVs pay for that.  Sharded handles use the lists when the fused exchange
 // carries every rank's displacement bound (api.cu), the full pass otherwise.
 // Bit 31 of a UAV's list-count word says "its external force may be non-zero": a pass must REPLACE every
 // UAV's force (SIM:356-358), but writing 24 zero bytes over 24 zero bytes for the (vast) majority without a
@@ -229,7 +231,8 @@ DEV void process_pair(const DevState& s, const DevGrid& g, int crash_mode, doubl
 }
 
 // SIM:356-358: forces replace external_force_ for the next tick (zero in crash mode, SIM:315-319)
-#define NL_LIVE 0x80000000u  // bit 31 of nl_count[]: the UAV's external force may be non-zero
+#define NL_LIVE 0x80000000u     // bit 31 of nl_count[]: the UAV's external force may be non-zero
+#define NL_CROWDED 0x40000000u  // bit 30: more than MRSB_NL_CAP candidates; nl_items[0][uav] = its record in the table
 DEV void store_result(const DevState& s, int64_t li, const PairAcc& acc) {
   s.fext[tix(F3_ROWS, 0, li)] = acc.fx;
   s.fext[tix(F3_ROWS, 1, li)] = acc.fy;
@@ -243,10 +246,8 @@ DEV bool nonzero(const PairAcc& acc) {
 #ifndef MRSB_COLLIDE_MINB
 #define MRSB_COLLIDE_MINB 7  // 71 registers, no spills; 8 and 10 (64 / 48 registers) measured no faster
 #endif
-// The full pass: every record against its stencil.  `only_if`: nullptr, or a device word that must
-// be non-zero for the kernel to do anything (the neighbour-list overflow fall-back).
-__global__ void __launch_bounds__(128, MRSB_COLLIDE_MINB) collide_kernel(DevState s, DevGrid g, int crash_mode, double rebounce, const uint32_t* only_if) {
-  if (only_if && *only_if == 0u) return;
+// The full pass: every record against its stencil (handles without neighbour lists).
+__global__ void __launch_bounds__(128, MRSB_COLLIDE_MINB) collide_kernel(DevState s, DevGrid g, int crash_mode, double rebounce) {
   const int64_t p = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (p >= int64_t(g.begin[g.n_buckets])) return;  // beyond the primary records (the mirror buckets hold copies)
   const double4 q  = g.rec[p];
@@ -352,27 +353,82 @@ __global__ void __launch_bounds__(128, MRSB_COLLIDE_MINB) build_lists_kernel(Dev
       for (uint32_t t = st.lo[k] + 1; t < st.hi[k]; t++) take(g.rec[t], k);
     }
   }
-  g.nl_count[li] = min(cnt, uint32_t(MRSB_NL_CAP)) | (g.nl_count[li] & NL_LIVE);
-  if (cnt > MRSB_NL_CAP) {  // too crowded for the lists: this pass and the next ones run the full kernel
-    g.ctl->overflow = 1u;
-    g.ctl->valid    = 0u;
+  const uint32_t live = g.nl_count[li] & NL_LIVE;
+  if (cnt > MRSB_NL_CAP) {
+    // too crowded for a list: remember the record instead (check_crowded walks its stencil every pass)
+    g.nl_items[li] = int32_t(uint32_t(p));
+    g.nl_count[li] = NL_CROWDED | live;
+    atomicAdd(&g.ctl->n_crowded, 1u);
+  } else {
+    g.nl_count[li] = cnt | live;
+  }
+}
+
+// A UAV without a list: every record of the stencil around its BUILD-TIME position, tested at the
+// candidates' CURRENT positions (the table only says who they are).  Same structure as collide_kernel.
+DEV void check_crowded(const DevState& s, const DevGrid& g, int crash_mode, double rebounce, int64_t gi, uint32_t rec_index, PairAcc& acc) {
+  const double4 qb = g.rec[rec_index];
+  const Stencil st = stencil_of(g, qb.x, qb.y, qb.z);
+  const double* qp = s.gpos + 3 * gi;
+  const double  qx = qp[0], qy = qp[1], qz = qp[2];
+  auto in_ball = [&](const double4& r, int k) {  // r: the candidate's record (build-time position: decides the row it was filed under)
+    const int64_t gj = __double_as_longlong(r.w);
+    if (gj == gi) return false;
+    if (cell_of(r.y, g.inv_cell) != st.rcy[k] || cell_of(r.z, g.inv_cell) != st.rcz[k]) return false;  // bucket alias / duplicate
+    const double* rp = s.gpos + 3 * gj;
+    return nf_dist2(qx, qy, qz, rp[0], rp[1], rp[2]) < 3.0;
+  };
+  const DevParams* __restrict__ Pi = s.params + s.pset[gi];
+  auto process = [&](int64_t gj) {
+    const double* rp = s.gpos + 3 * gj;
+    process_pair(s, g, crash_mode, rebounce, gi, qx, qy, qz, Pi, gj, rp[0], rp[1], rp[2], acc);
+  };
+  int     n_ball = 0;
+  int64_t h0 = 0, h1 = 0;
+  for (int k = 0; k < 4; k++)
+    for (uint32_t t = st.lo[k]; t < st.hi[k]; t++) {
+      const double4 r = g.rec[t];
+      if (!in_ball(r, k)) continue;
+      if (n_ball == 0) h0 = __double_as_longlong(r.w);
+      if (n_ball == 1) h1 = __double_as_longlong(r.w);
+      n_ball++;
+    }
+  if (n_ball <= 2) {
+    if (n_ball >= 1) process(h0);
+    if (n_ball == 2) process(h1);
+    return;
+  }
+  int64_t last = -1;  // >= 3: ascending j
+  for (int c = 0; c < n_ball; c++) {
+    int64_t best = INT64_MAX;
+    for (int k = 0; k < 4; k++)
+      for (uint32_t t = st.lo[k]; t < st.hi[k]; t++) {
+        const double4 r  = g.rec[t];
+        const int64_t gj = __double_as_longlong(r.w);
+        if (gj <= last || gj >= best || !in_ball(r, k)) continue;
+        best = gj;
+      }
+    if (best == INT64_MAX) break;
+    process(best);
+    last = best;
   }
 }
 
 // One thread per UAV: the exact predicate on the CURRENT positions of the listed candidates.
 // (Tried and dropped: remembering each candidate's distance at build time and skipping the fetch while
 // d_build - 2 D is still above sqrt(3) — the extra dependent load cost more than the skipped gathers.)
-__global__ void __launch_bounds__(256) check_kernel(DevState s, DevGrid g, int crash_mode, double rebounce) {
-  if (g.ctl->overflow) return;  // collide_kernel did this pass
+__global__ void __launch_bounds__(256, 4) check_kernel(DevState s, DevGrid g, int crash_mode, double rebounce) {
   const int64_t li = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (li >= s.n) return;
   const uint32_t word = g.nl_count[li];
-  const uint32_t cnt  = word & ~NL_LIVE;
+  const uint32_t cnt  = word & ~(NL_LIVE | NL_CROWDED);
   // forces were written from outside since the last pass (this pass' index <= write_all_until): replace them all
   const bool     live = (word & NL_LIVE) || g.ctl->n_passes <= g.ctl->write_all_until;
-  if (cnt == 0u && !live) return;  // no candidate, force already zero
+  if ((word & ~NL_LIVE) == 0u && !live) return;  // no candidate, force already zero
   PairAcc acc;
-  if (cnt) {
+  if (word & NL_CROWDED) {
+    check_crowded(s, g, crash_mode, rebounce, li + s.shard_begin, uint32_t(g.nl_items[li]), acc);
+  } else if (cnt) {
     const int64_t gi = li + s.shard_begin;
     const double* qp = s.gpos + 3 * gi;
     const double  qx = qp[0], qy = qp[1], qz = qp[2];
@@ -427,13 +483,12 @@ __global__ void __launch_bounds__(256) check_kernel(DevState s, DevGrid g, int c
   const bool nz = nonzero(acc);
   if (live || nz) store_result(s, li, acc);
   else if (acc.crashed_me) s.flags[li] |= FLAG_CRASHED;
-  if (nz != bool(word & NL_LIVE)) g.nl_count[li] = cnt | (nz ? NL_LIVE : 0u);
+  if (nz != bool(word & NL_LIVE)) g.nl_count[li] = (word & ~NL_LIVE) | (nz ? NL_LIVE : 0u);
 }
 
 // Are the lists still good for the positions of this pass?  One thread.
 __global__ void decide_kernel(NlCtl* c, unsigned long long* pair_counter, double skin, int always, cudaGraphConditionalHandle handle, int has_handle) {
   *pair_counter = 0ull;  // pairs found by this pass
-  if (c->overflow) c->n_overflow_passes++;  // the previous pass fell back to collide_kernel
   const uint32_t bits = c->disp_max_bits;  // largest squared displacement of the stepping launch since the last pass (float, rounded up)
   c->disp_max_bits    = 0u;
   const double d      = __dsqrt_ru(double(__uint_as_float(bits)));  // NaN stays NaN
@@ -441,9 +496,9 @@ __global__ void decide_kernel(NlCtl* c, unsigned long long* pair_counter, double
   const bool   rebuild = always || c->force || !c->valid || !(__dmul_ru(2.0, D) <= skin);
   if (rebuild) {
     D           = 0.0;
-    c->force    = 0u;
-    c->valid    = 1u;
-    c->overflow = 0u;
+    c->force     = 0u;
+    c->valid     = 1u;
+    c->n_crowded = 0u;  // build_lists_kernel counts them again
     c->n_rebuilds++;
   }
   c->D_total = D;
@@ -485,7 +540,7 @@ int launch_collide(const DevState& s, const DevGrid& g, int crash_mode, double r
   if (n <= 0) return 0;
   cudaMemsetAsync(g.counters, 0, sizeof(unsigned long long), stream);
   const int own = launch_table(s, g, cub_tmp, cub_tmp_bytes, stream);
-  collide_kernel<<<unsigned((n + 127) / 128), 128, 0, stream>>>(s, g, crash_mode, rebounce, nullptr);
+  collide_kernel<<<unsigned((n + 127) / 128), 128, 0, stream>>>(s, g, crash_mode, rebounce);
   return own + 1;  // CUB's scan kernels and the memsets are not counted
 }
 
@@ -495,13 +550,12 @@ int launch_collide_decide(const DevGrid& g, int always, cudaGraphConditionalHand
   decide_kernel<<<1, 1, 0, stream>>>(g.ctl, g.counters, g.skin, always, handle, has_handle);
   return 1;
 }
-int launch_collide_rebuild(const DevState& s, const DevGrid& g, int crash_mode, double rebounce, void* cub_tmp, size_t cub_tmp_bytes, cudaStream_t stream) {
+int launch_collide_rebuild(const DevState& s, const DevGrid& g, void* cub_tmp, size_t cub_tmp_bytes, cudaStream_t stream) {
   const int64_t n = s.n_global;
   if (n <= 0) return 0;
   const int own = launch_table(s, g, cub_tmp, cub_tmp_bytes, stream);
   build_lists_kernel<<<unsigned((n + 127) / 128), 128, 0, stream>>>(s, g);
-  collide_kernel<<<unsigned((n + 127) / 128), 128, 0, stream>>>(s, g, crash_mode, rebounce, &g.ctl->overflow);
-  return own + 2;
+  return own + 1;
 }
 int launch_collide_check(const DevState& s, const DevGrid& g, int crash_mode, double rebounce, cudaStream_t stream) {
   if (s.n <= 0) return 0;

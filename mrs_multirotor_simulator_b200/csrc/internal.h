@@ -102,12 +102,12 @@ struct DevState {
 struct NlCtl {
   uint32_t disp_max_bits;  // written by the stepping kernel (DevState::disp_max points here)
   uint32_t force;          // host: positions changed behind the stepping kernel's back -> rebuild
-  uint32_t valid;          // lists exist and no UAV overflowed its list
-  uint32_t overflow;       // the last rebuild found a UAV with more than MRSB_NL_CAP candidates
+  uint32_t valid;          // lists exist
+  uint32_t n_crowded;      // UAVs with more than MRSB_NL_CAP candidates at the last rebuild (they walk the table instead)
   uint32_t rebuild;        // decision of the current pass
   uint32_t pad_;
   double   D_total;        // sum of the per-launch displacement bounds since the last rebuild
-  unsigned long long n_rebuilds, n_passes, n_overflow_passes;
+  unsigned long long n_rebuilds, n_passes, reserved_;
   unsigned long long write_all_until;  // host: passes up to this index must write every UAV's force (they were written from outside)
 };
 
@@ -141,7 +141,7 @@ int launch_step(const DevState& s, const DevParams* uniform_params, double dt, i
 int launch_collide(const DevState& s, const DevGrid& g, int crash_mode, double rebounce, void* cub_tmp, size_t cub_tmp_bytes, cudaStream_t stream);
 // the pass with neighbour lists: decide (always) | rebuild (body of the graph's conditional node) | check (always)
 int launch_collide_decide(const DevGrid& g, int always, cudaGraphConditionalHandle handle, int has_handle, cudaStream_t stream);
-int launch_collide_rebuild(const DevState& s, const DevGrid& g, int crash_mode, double rebounce, void* cub_tmp, size_t cub_tmp_bytes, cudaStream_t stream);
+int launch_collide_rebuild(const DevState& s, const DevGrid& g, void* cub_tmp, size_t cub_tmp_bytes, cudaStream_t stream);
 int launch_collide_check(const DevState& s, const DevGrid& g, int crash_mode, double rebounce, cudaStream_t stream);
 size_t collide_tmp_bytes(int64_t n_global);
 int launch_publish_positions(const DevState& s, cudaStream_t stream);

@@ -33,7 +33,7 @@ for label, count in (("first", ticks), ("second", ticks)):
     torch.cuda.synchronize()
     i1 = b.collision_info()
     out[label] = {"tick_us": a.elapsed_time(e) * 1000 / count, "rebuild_fraction": (i1["rebuilds"] - i0["rebuilds"]) / max(1, i1["passes"] - i0["passes"]),
-                  "overflow_passes": i1["overflow_passes"] - i0["overflow_passes"], "pairs_last": b.counters()["pairs"]}
+                  "crowded_uavs": i1["crowded_uavs"], "pairs_last": b.counters()["pairs"]}
     i0 = i1
 out["info"] = b.collision_info()
 # step kernel alone
