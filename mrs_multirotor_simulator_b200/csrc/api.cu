@@ -465,7 +465,7 @@ int mrsb_destroy(mrsb_handle h) {
   void* ptrs[] = {h->ds.st,     h->ds.vprev,  h->ds.rpm,      h->ds.pid,      h->ds.fext,         h->ds.mext,       h->ds.imu,    h->ds.initz,
                   h->ds.cmd,    h->ds.ff,     h->ds.flags,    h->ds.mode,     h->ds.gpos,         h->d_params,      h->d_pset,    h->d_stage,
                   h->d_idx,     h->grid.bucket, h->grid.rank, h->grid.count, h->grid.aabb, h->grid.begin, h->grid.rec, h->grid.pairs,
-                  h->grid.counters, h->cub_tmp, h->grid.nl_count, h->grid.nl_items, h->grid.ctl};
+                  h->grid.counters, h->cub_tmp, h->grid.nl_count, h->grid.nl_items, h->grid.nl_active, h->grid.ctl};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -596,13 +596,14 @@ int mrsb_create(const mrsb_create_info* info, mrsb_handle* out) {
     g.pair_cap = int64_t(std::max<size_t>(4096, 4 * size_t(std::max<int64_t>(s.n, 1))));
     CREATE_RC(dalloc(&g.pairs, 2 * size_t(g.pair_cap)));
     CREATE_RC(dalloc(&g.counters, 4));
-    h->cub_tmp_bytes = collide_tmp_bytes(int64_t(g.n_buckets) + 3);
+    h->cub_tmp_bytes = collide_tmp_bytes(int64_t(g.n_buckets) + 3, s.n);
     CREATE_CU(cudaMalloc(&h->cub_tmp, std::max<size_t>(h->cub_tmp_bytes, 16)));
     // neighbour lists: single-shard handles now, sharded ones once the fused exchange is up (setup_p2p)
     if (s.n > 0 && !getenv("MRSB_NO_NEIGHBOUR_LISTS")) {
       g.nl_ld = s.ld;
       CREATE_RC(dalloc(&g.nl_count, size_t(g.nl_ld)));
       CREATE_RC(dalloc(&g.nl_items, size_t(MRSB_NL_CAP) * size_t(g.nl_ld)));
+      CREATE_RC(dalloc(&g.nl_active, size_t(g.nl_ld)));
       CREATE_RC(dalloc(&g.ctl, 1));
       CREATE_CU(cudaMemsetAsync(g.ctl, 0, sizeof(NlCtl), h->stream));
       CREATE_CU(cudaHostAlloc(&h->h_one, 2 * sizeof(uint32_t), cudaHostAllocDefault));
@@ -1136,6 +1137,7 @@ static int forces_written(mrsb_sim* h) {
   const unsigned long long until = (unsigned long long)h->list_passes + 1ull;  // index of the next pass that goes through decide_kernel
   CU(cudaMemcpyAsync(&h->grid.ctl->write_all_until, &until, sizeof(until), cudaMemcpyHostToDevice, h->stream));
   CU(cudaStreamSynchronize(h->stream));  // `until` lives on this stack frame
+  h->positions_touched = true;           // that pass rebuilds: UAVs without candidates are only visited by a rebuild
   return MRSB_OK;
 }
 

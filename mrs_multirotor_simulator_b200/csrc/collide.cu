@@ -45,6 +45,9 @@
 // the records there are a superset of its possible neighbours for as long as the lists are valid —
 // testing each candidate's CURRENT position (`check_crowded`).  Only the crowded UAVs pay for that.  Sharded handles use the lists when the fused exchange
 // carries every rank's displacement bound (api.cu), the full pass otherwise.
+// After a rebuild the UAVs that have anything to check (a candidate, or the crowded mark) are
+// compacted, in index order, into `nl_active` (CUB DeviceSelect): a list-only pass runs over those
+// only — typically a third of the swarm — with every lane busy.
 // Bit 31 of a UAV's list-count word says "its external force may be non-zero": a pass must REPLACE every
 // UAV's force (SIM:356-358), but writing 24 zero bytes over 24 zero bytes for the (vast) majority without a
 // neighbour is most of a list-only pass — a UAV with an empty list and a clear bit is left alone.  Whoever
@@ -54,6 +57,8 @@
 // owner of i evaluates the mirrored test d2 < ((arm_j+prop_j)+arm_i)+prop_i — the exact threshold
 // the owner of j uses for the directed pair (j,i) — and marks i itself.
 #include <cub/device/device_scan.cuh>
+#include <cub/device/device_select.cuh>
+#include <thrust/iterator/counting_iterator.h>
 
 #include "internal.h"
 
@@ -353,7 +358,15 @@ __global__ void __launch_bounds__(128, MRSB_COLLIDE_MINB) build_lists_kernel(Dev
       for (uint32_t t = st.lo[k] + 1; t < st.hi[k]; t++) take(g.rec[t], k);
     }
   }
-  const uint32_t live = g.nl_count[li] & NL_LIVE;
+  uint32_t live = g.nl_count[li] & NL_LIVE;
+  if (cnt == 0u && (live || g.ctl->n_passes <= g.ctl->write_all_until)) {
+    // nobody within the list radius: this UAV is not visited again until the next rebuild, so its force
+    // (left from an earlier collision, or written from outside) is replaced by zero right here (SIM:356-358)
+    s.fext[tix(F3_ROWS, 0, li)] = 0.0;
+    s.fext[tix(F3_ROWS, 1, li)] = 0.0;
+    s.fext[tix(F3_ROWS, 2, li)] = 0.0;
+    live                        = 0u;
+  }
   if (cnt > MRSB_NL_CAP) {
     // too crowded for a list: remember the record instead (check_crowded walks its stencil every pass)
     g.nl_items[li] = int32_t(uint32_t(p));
@@ -414,17 +427,14 @@ DEV void check_crowded(const DevState& s, const DevGrid& g, int crash_mode, doub
   }
 }
 
-// One thread per UAV: the exact predicate on the CURRENT positions of the listed candidates.
+// One UAV that has something to check: the exact predicate on the CURRENT positions of its listed candidates.
 // (Tried and dropped: remembering each candidate's distance at build time and skipping the fetch while
 // d_build - 2 D is still above sqrt(3) — the extra dependent load cost more than the skipped gathers.)
-__global__ void __launch_bounds__(256, 4) check_kernel(DevState s, DevGrid g, int crash_mode, double rebounce) {
-  const int64_t li = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (li >= s.n) return;
+DEV void check_one(const DevState& s, const DevGrid& g, int crash_mode, double rebounce, int64_t li) {
   const uint32_t word = g.nl_count[li];
   const uint32_t cnt  = word & ~(NL_LIVE | NL_CROWDED);
   // forces were written from outside since the last pass (this pass' index <= write_all_until): replace them all
   const bool     live = (word & NL_LIVE) || g.ctl->n_passes <= g.ctl->write_all_until;
-  if ((word & ~NL_LIVE) == 0u && !live) return;  // no candidate, force already zero
   PairAcc acc;
   if (word & NL_CROWDED) {
     check_crowded(s, g, crash_mode, rebounce, li + s.shard_begin, uint32_t(g.nl_items[li]), acc);
@@ -486,6 +496,18 @@ __global__ void __launch_bounds__(256, 4) check_kernel(DevState s, DevGrid g, in
   if (nz != bool(word & NL_LIVE)) g.nl_count[li] = (word & ~NL_LIVE) | (nz ? NL_LIVE : 0u);
 }
 
+
+// A list-only pass: the compacted UAVs that have something to check, grid-stride.
+__global__ void __launch_bounds__(256, 4) check_kernel(DevState s, DevGrid g, int crash_mode, double rebounce) {
+  const uint32_t n_active = g.ctl->n_active;
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n_active; k += gridDim.x * blockDim.x) check_one(s, g, crash_mode, rebounce, g.nl_active[k]);
+}
+
+struct HasWork {
+  const uint32_t* nl_count;
+  __device__ bool operator()(int32_t li) const { return (nl_count[li] & ~NL_LIVE) != 0u; }
+};
+
 // Are the lists still good for the positions of this pass?  One thread.
 __global__ void decide_kernel(NlCtl* c, unsigned long long* pair_counter, double skin, int always, cudaGraphConditionalHandle handle, int has_handle) {
   *pair_counter = 0ull;  // pairs found by this pass
@@ -499,6 +521,7 @@ __global__ void decide_kernel(NlCtl* c, unsigned long long* pair_counter, double
     c->force     = 0u;
     c->valid     = 1u;
     c->n_crowded = 0u;  // build_lists_kernel counts them again
+    c->n_active  = 0u;  // ... and the compaction after it
     c->n_rebuilds++;
   }
   c->D_total = D;
@@ -509,10 +532,12 @@ __global__ void decide_kernel(NlCtl* c, unsigned long long* pair_counter, double
 
 }  // namespace
 
-size_t collide_tmp_bytes(int64_t n_items) {
-  size_t bytes = 0;
-  cub::DeviceScan::ExclusiveSum(nullptr, bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, int(n_items));
-  return bytes;
+size_t collide_tmp_bytes(int64_t n_items, int64_t n_local) {
+  size_t scan = 0, select = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, scan, (const uint32_t*)nullptr, (uint32_t*)nullptr, int(n_items));
+  cub::DeviceSelect::If(nullptr, select, thrust::counting_iterator<int32_t>(0), (int32_t*)nullptr, (uint32_t*)nullptr, int(std::max<int64_t>(n_local, 1)),
+                        HasWork{nullptr});
+  return std::max(scan, select);
 }
 
 // table build: [box_reset, box,] count, scan, scatter.  Returns the number of own kernels.
@@ -555,10 +580,12 @@ int launch_collide_rebuild(const DevState& s, const DevGrid& g, void* cub_tmp, s
   if (n <= 0) return 0;
   const int own = launch_table(s, g, cub_tmp, cub_tmp_bytes, stream);
   build_lists_kernel<<<unsigned((n + 127) / 128), 128, 0, stream>>>(s, g);
+  // the UAVs with something to check, in index order
+  cub::DeviceSelect::If(cub_tmp, cub_tmp_bytes, thrust::counting_iterator<int32_t>(0), g.nl_active, &g.ctl->n_active, int(s.n), HasWork{g.nl_count}, stream);
   return own + 1;
 }
 int launch_collide_check(const DevState& s, const DevGrid& g, int crash_mode, double rebounce, cudaStream_t stream) {
   if (s.n <= 0) return 0;
-  check_kernel<<<unsigned((s.n + 255) / 256), 256, 0, stream>>>(s, g, crash_mode, rebounce);
+  check_kernel<<<unsigned(std::min<int64_t>((s.n + 255) / 256, 148 * 4)), 256, 0, stream>>>(s, g, crash_mode, rebounce);
   return 1;
 }

@@ -103,9 +103,9 @@ struct NlCtl {
   uint32_t disp_max_bits;  // written by the stepping kernel (DevState::disp_max points here)
   uint32_t force;          // host: positions changed behind the stepping kernel's back -> rebuild
   uint32_t valid;          // lists exist
+  uint32_t n_active;       // entries of DevGrid::nl_active (UAVs with something to check on list-only passes)
   uint32_t n_crowded;      // UAVs with more than MRSB_NL_CAP candidates at the last rebuild (they walk the table instead)
   uint32_t rebuild;        // decision of the current pass
-  uint32_t pad_;
   double   D_total;        // sum of the per-launch displacement bounds since the last rebuild
   unsigned long long n_rebuilds, n_passes, reserved_;
   unsigned long long write_all_until;  // host: passes up to this index must write every UAV's force (they were written from outside)
@@ -122,6 +122,7 @@ struct DevGrid {
   uint32_t* nl_count;   // [nl_ld] candidates of each local UAV; bit 31: its external force may be non-zero (nullptr: no lists)
   int32_t*  nl_items;   // [MRSB_NL_CAP][nl_ld] their global indices, slot-major
   int64_t   nl_ld;
+  int32_t*  nl_active;  // [n_local] local indices of the UAVs with a candidate (or the crowded mark), ascending
   NlCtl*    ctl;
   uint32_t* bucket;     // [n_global] bucket of each UAV, 0xFFFFFFFF = not inserted (remote and outside this shard's box)
   uint32_t* rank;       // [n_global] arrival rank inside its bucket
@@ -143,7 +144,7 @@ int launch_collide(const DevState& s, const DevGrid& g, int crash_mode, double r
 int launch_collide_decide(const DevGrid& g, int always, cudaGraphConditionalHandle handle, int has_handle, cudaStream_t stream);
 int launch_collide_rebuild(const DevState& s, const DevGrid& g, void* cub_tmp, size_t cub_tmp_bytes, cudaStream_t stream);
 int launch_collide_check(const DevState& s, const DevGrid& g, int crash_mode, double rebounce, cudaStream_t stream);
-size_t collide_tmp_bytes(int64_t n_global);
+size_t collide_tmp_bytes(int64_t n_buckets, int64_t n_local);
 int launch_publish_positions(const DevState& s, cudaStream_t stream);
 // cross-GPU hand-shake of the fused exchange: tell every peer "my positions of `epoch` have landed", wait for theirs
 // `disp` (may be nullptr): this rank's displacement word — sent along with the epoch, and raised to the largest of all ranks' by the wait
