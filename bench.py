@@ -151,7 +151,38 @@ def cpu_reference(n_sample, ticks, warmup, threads):
     dt = time.perf_counter() - t0
     desc = (f"{n_sample} UAVs (first rows of the 1 Mi grid) x {ticks} ticks, {threads} threads; stepping = oracle port (-O2 -ffp-contract=off), "
             f"collisions = {'real vendored nanoflann (KD-tree build 1 thread, queries threaded)' if engine == 'nanoflann' else 'cell-list port'}")
+    desc += "; " + port_vs_reference_sources()
     return n_sample * ticks / dt, dt / ticks * 1e3, desc
+
+
+_PORT_CHECK = None
+
+
+def port_vs_reference_sources(n=2048, ticks=20):
+    """The timed port against the reference's OWN UavSystem sources compiled against the Eigen/odeint stand-ins
+    (oracle/_ref/libref_uavsystem.so, built where /root/reference exists and shipped): same bits, and how fast each is."""
+    global _PORT_CHECK
+    if _PORT_CHECK is None:
+        from oracle import binding as O
+
+        if O.refsys_lib() is None:
+            _PORT_CHECK = "reference-sources build (oracle/_ref/libref_uavsystem.so) not shipped: port not re-verified in this run"
+        else:
+            spawn, cmd = workload(0, n)
+            rate = {}
+            state = {}
+            for name, cls in (("port", O.OracleSwarm), ("reference sources", O.RefSwarm)):
+                sw = cls([x500_world()], spawn_xyz=spawn, n=n)
+                sw.set_input(O.VELOCITY_HDG_RATE_CMD, cmd)
+                t0 = time.perf_counter()
+                sw.make_step(DT, ticks, 1)
+                rate[name] = n * ticks / (time.perf_counter() - t0)
+                state[name] = sw.get_state()
+            same = all(np.array_equal(state["port"][k], state["reference sources"][k]) for k in state["port"])
+            _PORT_CHECK = (f"port {'bit-identical to' if same else 'DIFFERS from'} the reference's own UavSystem sources compiled against Eigen/odeint stand-ins "
+                           f"on {n} UAVs x {ticks} ticks (1 thread: port {rate['port'] / 1e6:.2f} M, reference sources {rate['reference sources'] / 1e6:.2f} M UAV-steps/s; "
+                           f"the faster one is the baseline)")
+    return _PORT_CHECK
 
 
 def run_reference(args):
