@@ -840,7 +840,7 @@ static int exchange_positions(mrsb_sim* h) {
     // the step kernel already stored this shard's positions into every peer's buffer: only the
     // hand-shake "my epoch has landed" / "everybody's has" is left
     uint32_t* disp = h->lists_on ? &h->grid.ctl->disp_max_bits : nullptr;
-    h->n_launches += launch_p2p_signal(h->d_peer_flags, h->n_ranks, h->rank, h->epoch, disp, h->stream);
+    h->n_launches += launch_p2p_signal(h->d_peer_flags, h->n_ranks, h->rank, h->epoch, disp, h->ds.n > 0 ? 0xFFFFFFFFu : 0u, h->stream);
     h->n_launches += launch_p2p_wait(h->d_flags, h->n_ranks, h->rank, h->epoch, h->h_status, disp, h->stream);
     return MRSB_OK;
   }

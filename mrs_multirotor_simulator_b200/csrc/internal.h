@@ -147,8 +147,10 @@ int launch_collide_check(const DevState& s, const DevGrid& g, int crash_mode, do
 size_t collide_tmp_bytes(int64_t n_buckets, int64_t n_local);
 int launch_publish_positions(const DevState& s, cudaStream_t stream);
 // cross-GPU hand-shake of the fused exchange: tell every peer "my positions of `epoch` have landed", wait for theirs
-// `disp` (may be nullptr): this rank's displacement word — sent along with the epoch, and raised to the largest of all ranks' by the wait
-int launch_p2p_signal(unsigned long long* const* peer_flags, int n_ranks, int rank, unsigned long long epoch, const uint32_t* disp, cudaStream_t stream);
+// `disp`: this rank's displacement word — sent along with the epoch, and raised to the largest of all ranks' by the wait.
+// A rank that does not track it (nullptr) sends `disp_if_untracked` instead: "unbounded", or 0 if it has no UAVs at all.
+int launch_p2p_signal(unsigned long long* const* peer_flags, int n_ranks, int rank, unsigned long long epoch, const uint32_t* disp,
+                      uint32_t disp_if_untracked, cudaStream_t stream);
 int launch_p2p_wait(const unsigned long long* flags, int n_ranks, int rank, unsigned long long epoch, int* status, uint32_t* disp, cudaStream_t stream);
 
 int launch_scatter_input(const DevState& s, int mode, int64_t n, const int32_t* idx_dev, const double* payload_dev, int stride, cudaStream_t stream);

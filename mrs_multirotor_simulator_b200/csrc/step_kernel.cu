@@ -41,10 +41,12 @@ __global__ void publish_positions_kernel(DevState s) {
 // Flag block of a rank: [0, G) epochs written by the peers; [G, 3G) the peers' displacement words
 // (float bits of the largest squared displacement of their stepping launch), double-buffered by epoch
 // parity — a peer is at most one tick ahead, so the slot of epoch e is not overwritten before e + 2.
-__global__ void p2p_signal_kernel(unsigned long long* const* peer_flags, int n_ranks, int rank, unsigned long long epoch, const uint32_t* disp) {
+__global__ void p2p_signal_kernel(unsigned long long* const* peer_flags, int n_ranks, int rank, unsigned long long epoch, const uint32_t* disp,
+                                  uint32_t disp_if_untracked) {
   const int r = threadIdx.x;
-  if (disp && r < n_ranks && r != rank)
-    *reinterpret_cast<volatile unsigned long long*>(peer_flags[r] + n_ranks + 2 * rank + int(epoch & 1ull)) = (unsigned long long)*disp;
+  if (r < n_ranks && r != rank)
+    *reinterpret_cast<volatile unsigned long long*>(peer_flags[r] + n_ranks + 2 * rank + int(epoch & 1ull)) =
+        (unsigned long long)(disp ? *disp : disp_if_untracked);
   __threadfence_system();
   if (r < n_ranks && r != rank) *reinterpret_cast<volatile unsigned long long*>(peer_flags[r] + rank) = epoch;
 }
@@ -73,8 +75,9 @@ __global__ void p2p_wait_kernel(const unsigned long long* flags, int n_ranks, in
 }
 }  // namespace
 
-int launch_p2p_signal(unsigned long long* const* peer_flags, int n_ranks, int rank, unsigned long long epoch, const uint32_t* disp, cudaStream_t stream) {
-  p2p_signal_kernel<<<1, 32, 0, stream>>>(peer_flags, n_ranks, rank, epoch, disp);
+int launch_p2p_signal(unsigned long long* const* peer_flags, int n_ranks, int rank, unsigned long long epoch, const uint32_t* disp,
+                      uint32_t disp_if_untracked, cudaStream_t stream) {
+  p2p_signal_kernel<<<1, 32, 0, stream>>>(peer_flags, n_ranks, rank, epoch, disp, disp_if_untracked);
   return 1;
 }
 int launch_p2p_wait(const unsigned long long* flags, int n_ranks, int rank, unsigned long long epoch, int* status, uint32_t* disp, cudaStream_t stream) {
