@@ -509,25 +509,30 @@ struct HasWork {
 };
 
 // Are the lists still good for the positions of this pass?  One thread.
-__global__ void decide_kernel(NlCtl* c, unsigned long long* pair_counter, double skin, int always, cudaGraphConditionalHandle handle, int has_handle) {
-  *pair_counter = 0ull;  // pairs found by this pass
-  const uint32_t bits = c->disp_max_bits;  // largest squared displacement of the stepping launch since the last pass (float, rounded up)
-  c->disp_max_bits    = 0u;
-  const double d      = __dsqrt_ru(double(__uint_as_float(bits)));  // NaN stays NaN
-  double       D      = __dadd_ru(c->D_total, d);
-  const bool   rebuild = always || c->force || !c->valid || !(__dmul_ru(2.0, D) <= skin);
+__global__ void decide_kernel(NlCtl* __restrict__ c, unsigned long long* __restrict__ pair_counter, double skin, int always,
+                              cudaGraphConditionalHandle handle, int has_handle) {
+  // every load first (they are independent: one round trip), then the decision, then the stores
+  const uint32_t           bits  = c->disp_max_bits;  // largest squared displacement of the stepping launch since the last pass (float, rounded up)
+  const double             D_old = c->D_total;
+  const uint32_t           force = c->force, valid = c->valid;
+  const unsigned long long n_rebuilds = c->n_rebuilds, n_passes = c->n_passes;
+  const double d       = __dsqrt_ru(double(__uint_as_float(bits)));  // NaN stays NaN
+  double       D       = __dadd_ru(D_old, d);
+  const bool   rebuild = always || force || !valid || !(__dmul_ru(2.0, D) <= skin);
+  if (has_handle) cudaGraphSetConditional(handle, rebuild ? 1u : 0u);
+  *pair_counter    = 0ull;  // pairs found by this pass
+  c->disp_max_bits = 0u;
   if (rebuild) {
-    D           = 0.0;
+    D            = 0.0;
     c->force     = 0u;
     c->valid     = 1u;
     c->n_crowded = 0u;  // build_lists_kernel counts them again
     c->n_active  = 0u;  // ... and the compaction after it
-    c->n_rebuilds++;
+    c->n_rebuilds = n_rebuilds + 1ull;
   }
-  c->D_total = D;
-  c->rebuild = rebuild ? 1u : 0u;
-  c->n_passes++;
-  if (has_handle) cudaGraphSetConditional(handle, rebuild ? 1u : 0u);
+  c->D_total  = D;
+  c->rebuild  = rebuild ? 1u : 0u;
+  c->n_passes = n_passes + 1ull;
 }
 
 }  // namespace
