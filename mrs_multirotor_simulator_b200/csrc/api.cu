@@ -156,6 +156,7 @@ struct mrsb_sim {
   bool     positions_touched   = true;  // positions were written by something else than ONE stepping launch
   int      rebuild_own         = 0;     // own kernels of one rebuild (for the launch counter)
   int64_t  list_passes         = 0;     // passes that went through decide_kernel (it counts them too: NlCtl::n_passes)
+  bool     list_graph_failed   = false; // conditional graph nodes unavailable: do not try again on every pass
   int64_t  rebuilds_counted    = 0;
   uint32_t* h_one              = nullptr;  // pinned constant 1 (source of the async "force rebuild" copy)
 
@@ -914,7 +915,10 @@ static int collide_local(mrsb_sim* h) {
     h->positions_touched = false;
     h->steps_since_pass  = 0;
     h->list_passes++;
-    if (!h->coll_graph[k] && !getenv("MRSB_NO_GRAPH")) h->coll_graph[k] = build_list_graph(h, &h->coll_graph_own[k], &h->rebuild_own);
+    if (!h->coll_graph[k] && !h->list_graph_failed && !getenv("MRSB_NO_GRAPH")) {
+      h->coll_graph[k]     = build_list_graph(h, &h->coll_graph_own[k], &h->rebuild_own);
+      h->list_graph_failed = h->coll_graph[k] == nullptr;
+    }
     if (h->coll_graph[k]) {
       CU(cudaGraphLaunch(h->coll_graph[k], h->stream));
       h->n_launches += h->coll_graph_own[k];  // the rebuilds are added from the device-side count (mrsb_get_counters)
