@@ -285,18 +285,28 @@ def run_b200(args):
         batch.handle_collisions()
 
     def timed_loop(fn, steps):
-        """K steps, each bracketed by its own event pair on the handle's stream; returns total ms (max over ranks)."""
-        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        """K steps timed with CUDA events on the handle's stream; returns total ms (max over ranks).  When the
+        per-GPU working set exceeds L2 there is nothing to flush and ONE event pair brackets all K steps;
+        otherwise every step has its own pair and the L2 flush runs between the pairs."""
         barrier()
-        for a, b in ev:
-            if flush:
+        if not flush:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            for _ in range(steps):
+                fn()
+            b.record(stream)
+            barrier()
+            ms = a.elapsed_time(b)
+        else:
+            ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+            for a, b in ev:
                 with torch.cuda.stream(stream):
                     flush_buf.zero_()
-            a.record(stream)
-            fn()
-            b.record(stream)
-        barrier()
-        ms = sum(a.elapsed_time(b) for a, b in ev)
+                a.record(stream)
+                fn()
+                b.record(stream)
+            barrier()
+            ms = sum(a.elapsed_time(b) for a, b in ev)
         if dist is not None:
             t = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{local}")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -145,8 +145,9 @@ struct mrsb_sim {
   cudaEvent_t  ev_up[2] = {nullptr, nullptr}, ev_applied[2] = {nullptr, nullptr}, ev_snap[2] = {nullptr, nullptr}, ev_down[2] = {nullptr, nullptr};
   uint64_t     n_up = 0, n_down = 0;
 
-  // the collision pass is a fixed sequence of 7 launches with fixed arguments: replayed as a CUDA graph
-  // (one per gather-buffer parity); invalidated when its arguments change
+  // the collision pass is a fixed set of launches with fixed arguments: replayed as a CUDA graph (one per
+  // gather-buffer parity; with neighbour lists the table rebuild sits in a conditional node of it);
+  // invalidated when its arguments change
   cudaGraphExec_t coll_graph[2]     = {nullptr, nullptr};
   int             coll_graph_own[2] = {0, 0};  // own kernels per replay (for the launch counter)
 

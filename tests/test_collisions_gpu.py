@@ -171,8 +171,13 @@ def _row_hash(cy, cz):
 
 
 def test_stencil_row_across_the_end_of_the_bucket_table():
-    """Two x-adjacent cells whose buckets are B-1 and 0: found through the mirror bucket."""
-    n_buckets = 1024  # smallest table (n_global <= 512)
+    """Two x-adjacent cells whose buckets are B-1 and 0: found through the mirror bucket.  Cell edge and
+    table size are read back from the library (they depend on how the pass is organised)."""
+    from mrs_multirotor_simulator_b200 import UavBatch
+
+    probe = UavBatch([af("x500")], spawn_xyz=np.zeros((24, 3)), n=24)
+    info = probe.collision_info()
+    cell, n_buckets = info["cell"], info["n_buckets"]
     hits = []
     for cy in range(-40, 40):
         for cz in range(0, 4):
@@ -182,16 +187,24 @@ def test_stencil_row_across_the_end_of_the_bucket_table():
     assert len(hits) >= 4
     xyz = []
     for cx, cy, cz in hits[:8]:
-        xb = 4.0 * (cx + 1)  # boundary between cell cx and cx+1
-        y, z = 4.0 * cy + 2.0, 4.0 * cz + 2.0
+        xb = cell * (cx + 1)  # boundary between cell cx and cx+1
+        y, z = cell * cy + 0.5 * cell, cell * cz + 0.5 * cell
         xyz += [[xb - 0.2, y, z], [xb + 0.2, y, z], [xb + 0.45, y + 0.1, z]]
     xyz = np.array(xyz)
     n = len(xyz)
+    assert n == 24
     types = [af("x500")]
     tou = np.zeros(n, dtype=np.int32)
     arm, prop, mass = geometry(types, tou)
     ref_pairs, ref_forces, _ = O.collide_snapshot(xyz, arm, prop, mass, False, 100.0, engine=ENGINE)
     b, pairs, forces, _ = run_gpu_pass(types, tou, xyz, False, 100.0)
+    assert b.collision_info()["n_buckets"] == n_buckets
     assert len(ref_pairs) >= 4 * len(hits[:8])
     assert np.array_equal(sorted_pairs(ref_pairs), pairs)
     assert np.array_equal(ref_forces, forces)
+    # the same through the ageing table: one stepping launch, then a list-only pass
+    b.make_step(0.01)
+    b.handle_collisions()
+    x = b.get_state()["x"]
+    ref_pairs, _, _ = O.collide_snapshot(x, arm, prop, mass, False, 100.0, engine=ENGINE)
+    assert np.array_equal(sorted_pairs(ref_pairs), b.get_collision_pairs())
