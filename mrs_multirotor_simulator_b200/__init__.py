@@ -7,4 +7,5 @@ from .airframes import AIRFRAMES, CONTROLLER_DEFAULTS, SIMULATOR_DEFAULTS, airfr
 from .batch import (ACCELERATION_HDG_CMD, ACCELERATION_HDG_RATE_CMD, ACTUATOR_CMD, ATTITUDE_CMD, ATTITUDE_RATE_CMD,  # noqa: F401
                     CONTROL_GROUP_CMD, INPUT_UNKNOWN, POSITION_CMD, STRIDE, TILT_HDG_RATE_CMD, VELOCITY_HDG_CMD,
                     VELOCITY_HDG_RATE_CMD, UavBatch, model_params)
+from .scenario import Scenario, load_scenario, scenario_from_tree  # noqa: F401
 from .uav_system import UavSystem  # noqa: F401
