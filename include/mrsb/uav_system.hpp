@@ -162,6 +162,9 @@ public:
     if (n) check(mrsb_get_collision_pairs(h_, out.front().data(), n, &n));
     return out;
   }
+  // after writing through mrsb_get_device_view: positions / external forces were changed behind the library's back
+  void positionsWritten() { check(mrsb_publish_positions(h_)); }
+  void forcesWritten() { check(mrsb_forces_written(h_)); }
   mrsb_handle handle() { return h_; }
 
 private:
