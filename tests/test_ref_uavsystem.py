@@ -290,3 +290,84 @@ def test_eigen_evaluation_order_sensitivity_is_far_below_the_tolerance():
     assert any(v > 0 for v in worst.values()), "the two builds are supposed to differ in rounding"
     for k, v in worst.items():
         assert v <= TOL[k] / 100.0, (k, v)
+
+
+# ------------------------------------------------------------------ randomised event sequences
+@pytest.mark.parametrize("seed", range(12))
+def test_random_event_sequences_bit_exact(seed):
+    """Fuzz: a random sequence of API calls (commands of every mode with ordinary, extreme and non-finite
+    payloads, feed-forwards, crashes, forces, moments, gains, setParams, state teleports) interleaved with
+    steps of varying dt on a mixed 4/6/8-motor swarm — the restatement must track the reference's own code
+    bit for bit through all of it."""
+    rng = np.random.default_rng(1000 + seed)
+    n = 12
+    frames = ["x500", "f550", "naki", "t650"]
+    types = [airframe(f, ground_enabled=bool(rng.integers(2)), ground_z=float(rng.uniform(-1, 1)), takeoff_patch_enabled=bool(rng.integers(2))) for f in frames]
+    tou = rng.integers(0, len(types), n).astype(np.int32)
+    spawn = np.stack([rng.uniform(-20, 20, n), rng.uniform(-20, 20, n), rng.uniform(0, 10, n)], axis=1)
+    orc, ref = pair(types, n, tou, spawn, heading=rng.uniform(-3.2, 3.2, n))
+
+    def payload(mode, k):
+        width = O.STRIDE[mode]
+        kind = rng.integers(6)
+        if kind == 0:  # ordinary flight-like values
+            p = _commands(mode, k, seed=int(rng.integers(1 << 30)))
+        elif kind == 1:
+            p = rng.uniform(-1, 1, (k, width))
+        elif kind == 2:
+            p = rng.uniform(-50, 50, (k, width))
+        elif kind == 3:
+            p = np.zeros((k, width))
+        elif kind == 4:
+            p = rng.uniform(-1e6, 1e6, (k, width))
+        else:
+            p = rng.uniform(-2, 2, (k, width))
+            bad = rng.integers(0, 4, (k, width))
+            p[bad == 0] = rng.choice([np.nan, np.inf, -np.inf, 0.0, -0.0])
+        return np.ascontiguousarray(p, dtype=np.float64)
+
+    for event in range(120):
+        what = rng.integers(12)
+        idx = np.sort(rng.choice(n, int(rng.integers(1, n + 1)), replace=False)).astype(np.int32)
+        if what <= 3:
+            mode = int(rng.choice(ALL_MODES))
+            pl = payload(mode, len(idx))
+            both(orc, ref, lambda s: s.set_input(mode, pl, idx=idx))
+        elif what == 4:
+            kind = int(rng.integers(4))
+            pl = rng.uniform(-2, 2, (len(idx), 4))
+            both(orc, ref, lambda s: s.set_feedforward(kind, pl, idx))
+        elif what == 5:
+            f = rng.uniform(-5, 5, (len(idx), 3))
+            both(orc, ref, lambda s: s.apply_force(f, idx))
+        elif what == 6:
+            m = rng.uniform(-0.05, 0.05, (len(idx), 3))
+            both(orc, ref, lambda s: s.set_external_moment(m, idx))
+        elif what == 7:
+            which = str(rng.choice(["mixer", "rate", "attitude", "velocity", "position"]))
+            vals = {"mixer": [float(rng.integers(2))], "rate": rng.uniform(0, 6, 3), "attitude": rng.uniform(0, 8, 5),
+                    "velocity": rng.uniform(0, 4, 4), "position": rng.uniform(0, 4, 4)}[which]
+            both(orc, ref, lambda s: s.set_controller_params(which, vals, idx))
+        elif what == 8 and rng.integers(3) == 0:
+            both(orc, ref, lambda s: s.crash(idx[:1]))
+        elif what == 9 and rng.integers(2) == 0:
+            # setParams keeps the airframe's motor count here (the reference would index motors out of range otherwise)
+            one = idx[:1]
+            f = frames[int(tou[one[0]])]
+            p = airframe(f, mass=float(airframe(f)["mass"] * rng.uniform(0.7, 1.4)), ground_enabled=bool(rng.integers(2)),
+                         ground_z=float(rng.uniform(-1, 1)), takeoff_patch_enabled=bool(rng.integers(2)))
+            both(orc, ref, lambda s: s.set_params(p, one))
+        elif what == 10 and rng.integers(2) == 0:
+            st = orc.get_state(idx)
+            x = st["x"] + rng.uniform(-1, 1, st["x"].shape)
+            v = rng.uniform(-3, 3, st["v"].shape)
+            both(orc, ref, lambda s: s.set_state(idx=idx, x=x, v=v, R=st["R"], omega=st["omega"], motor_rpm=st["motor_rpm"]))
+        elif what == 11:
+            both(orc, ref, lambda s: s.set_input(O.INPUT_UNKNOWN, None, idx[:1]))
+        dt = float(rng.choice([0.001, 0.004, 0.005, 0.01, 0.02]))
+        k = int(rng.integers(1, 12))
+        both(orc, ref, lambda s: s.make_step(dt, k))
+        assert_identical(orc, ref, f"seed {seed} event {event} (kind {what})", pid=False)
+        assert np.array_equal(orc.has_crashed(), ref.has_crashed())
+    for i in range(n):
+        assert np.array_equal(orc.get_pid_state(i), ref.get_pid_state(i), equal_nan=True), i
