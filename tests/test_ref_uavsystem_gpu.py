@@ -102,3 +102,74 @@ def test_c5_mixed_airframes_and_events_vs_compiled_reference():
         gpu.make_step(0.01)
     check(ref, gpu, "crash + force")
     assert np.all(gpu.get_state()["x"][[5, 6, 7], 2] == 0.0)  # the crashed ones fell onto the ground plane
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_event_sequences_vs_compiled_reference(seed):
+    """Fuzz with finite, flight-like payloads: random commands of every mode, feed-forwards, forces, moments,
+    gains, crashes, unknown input and setParams between steps of varying dt on a mixed 4/6/8-motor swarm.
+    After every event the CUDA state must be within tolerance of the reference's own code; it is then
+    re-synchronised to it (set_state), so that the open-loop modes' instability does not accumulate."""
+    rng = np.random.default_rng(2000 + seed)
+    n = 16
+    frames = ["x500", "f550", "naki", "t650"]
+    types = [af(f, ground_enabled=bool(rng.integers(2)), ground_z=float(rng.uniform(-1, 0)), takeoff_patch_enabled=bool(rng.integers(2))) for f in frames]
+    tou = rng.integers(0, len(types), n).astype(np.int32)
+    spawn = np.stack([rng.uniform(-20, 20, n), rng.uniform(-20, 20, n), rng.uniform(1, 10, n)], axis=1)
+    ref, gpu = make(types, tou, spawn, rng.uniform(-3.0, 3.0, n))
+    ff_names = ["acceleration_hdg_rate", "acceleration_hdg", "velocity_hdg", "velocity_hdg_rate"]
+    tol = {"x": 1e-9, "v": 1e-8, "R": 1e-9, "omega": 1e-6, "motor_rpm": 1e-5, "imu": 1e-4}
+    for event in range(40):
+        what = int(rng.integers(10))
+        idx = np.sort(rng.choice(n, int(rng.integers(1, n + 1)), replace=False)).astype(np.int32)
+        if what <= 3:
+            mode = int(rng.choice(ALL_MODES))
+            pl = _commands(mode, len(idx), seed=int(rng.integers(1 << 30)))
+            for s in (ref, gpu):
+                s.set_input(mode, pl, idx=idx)
+        elif what == 4:
+            kind = int(rng.integers(4))
+            pl = rng.uniform(-1, 1, (len(idx), 4))
+            ref.set_feedforward(kind, pl, idx)
+            gpu.set_feedforward(ff_names[kind], pl, idx)
+        elif what == 5:
+            f = rng.uniform(-3, 3, (len(idx), 3))
+            for s in (ref, gpu):
+                s.apply_force(f, idx)
+        elif what == 6:
+            m = rng.uniform(-0.02, 0.02, (len(idx), 3))
+            for s in (ref, gpu):
+                s.set_external_moment(m, idx)
+        elif what == 7:
+            which = str(rng.choice(["mixer", "rate", "attitude", "velocity", "position"]))
+            vals = {"mixer": [float(rng.integers(2))], "rate": rng.uniform(1, 5, 3), "attitude": rng.uniform(1, 8, 5),
+                    "velocity": rng.uniform(0.5, 4, 4), "position": rng.uniform(0.5, 4, 4)}[which]
+            for s in (ref, gpu):
+                s.set_controller_params(which, vals, idx)
+        elif what == 8:
+            if rng.integers(2):
+                for s in (ref, gpu):
+                    s.crash(idx[:1])
+            else:
+                for s in (ref, gpu):
+                    s.set_input(O.INPUT_UNKNOWN, None, idx[:1])
+        else:
+            one = idx[:1]
+            f = frames[int(tou[one[0]])]
+            p = af(f, mass=float(af(f)["mass"] * rng.uniform(0.8, 1.3)), ground_enabled=bool(rng.integers(2)), ground_z=float(rng.uniform(-1, 0)),
+                   takeoff_patch_enabled=bool(rng.integers(2)))
+            for s in (ref, gpu):
+                s.set_params(p, one)
+        dt = float(rng.choice([0.004, 0.005, 0.01]))
+        k = int(rng.integers(1, 8))
+        ref.make_step(dt, k)
+        for _ in range(k):
+            gpu.make_step(dt)
+        sr, sg = ref.get_state(), gpu.get_full_state()
+        for key, t in tol.items():
+            assert np.all(np.isfinite(sr[key])), (seed, event, key)
+            scale = 1.0 + float(np.max(np.abs(sr[key])))
+            d = float(np.max(np.abs(sr[key] - sg[key])))
+            assert d <= t * scale, f"seed {seed} event {event} (kind {what}) {key}: {d:.3e} > {t * scale:.1e}"
+        assert np.array_equal(np.asarray(ref.has_crashed()), np.asarray(gpu.has_crashed()))
+        gpu.set_state(x=sr["x"], v=sr["v"], R=sr["R"], omega=sr["omega"], motor_rpm=sr["motor_rpm"])
