@@ -424,9 +424,11 @@ def run_b200(args):
             "data": "synthetic", "config": dict(workload_config(world, l2_note), exchange=EXCHANGE[batch.exchange_mode()]), "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(cmd_host.numel() * 8), "d2h_bytes_per_step": int(pos_host[0].numel() * 8),
                     "steps": n_e2e, "blocking_api_value": N_UAVS * n_e2e / e2e_blocking_s,
+                    "h2d_gbs_achieved": cmd_host.numel() * 8 * n_e2e / e2e_s / 1e9, "d2h_gbs_achieved": pos_host[0].numel() * 8 * n_e2e / e2e_s / 1e9,
                     "note": "per rank, every tick, via the C ABI: VelocityHdgRate rows H2D from pinned memory (mrsb_set_input_async), makeStep, "
                             "handleCollisions, positions D2H to pinned memory (mrsb_get_positions_async); upload of tick t+1 and download of tick "
-                            "t-1 overlap tick t on separate streams; blocking_api_value = same with mrsb_set_input + mrsb_get_state"},
+                            "t-1 overlap tick t on separate streams (the tick is then as long as its PCIe upload: see h2d_gbs_achieved); "
+                            "blocking_api_value = same with mrsb_set_input + mrsb_get_state"},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)
     if dist is not None:
