@@ -93,3 +93,29 @@ def test_command_encoders_follow_references_hpp():
     assert U._encode(U.TiltHdgRate())[1] == [1.0, 0.0, 0.0, 0.0, 0.0]  # Vector3d::Identity() default (references.hpp:123)
     with pytest.raises(TypeError):
         U._encode(object())
+
+
+def test_neighbour_list_validity_argument_on_a_numpy_model():
+    """The invariant behind collide.cu's neighbour lists, checked on a host model: lists built with radius
+    sqrt(3) + skin stay a superset of the true neighbours (d^2 < 3) for as long as twice the SUM of the
+    per-tick maximum displacements stays <= skin — whatever the individual UAVs do."""
+    rng = np.random.default_rng(3)
+    n, skin = 400, 1.2
+    r_list = np.sqrt(3.0) + skin
+    x = rng.uniform(0, 40, (n, 3)) * [1, 1, 0.2]
+    def within(p, r2):
+        d2 = ((p[:, None, :] - p[None, :, :]) ** 2).sum(-1)
+        np.fill_diagonal(d2, np.inf)
+        return d2 < r2
+    lists, D, rebuilds, hits = within(x, r_list ** 2), 0.0, 0, 0
+    for tick in range(300):
+        step = rng.normal(0, 0.03, (n, 3)) + rng.choice([0.0, 0.15], (n, 1), p=[0.97, 0.03]) * rng.normal(0, 1, (n, 3))
+        x = x + step
+        D += float(np.sqrt((step ** 2).sum(-1)).max())
+        if 2.0 * D > skin:
+            lists, D = within(x, r_list ** 2), 0.0
+            rebuilds += 1
+        true = within(x, 3.0)
+        assert not np.any(true & ~lists), tick  # every true neighbour is still listed
+        hits += int(true.sum())
+    assert 0 < rebuilds < 150 and hits > 0
