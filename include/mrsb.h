@@ -198,6 +198,13 @@ int mrsb_set_feedforward_acceleration_hdg_rate(mrsb_handle h, int64_t n, const i
 int mrsb_set_feedforward_acceleration_hdg(mrsb_handle h, int64_t n, const int32_t* idx, const double* payload);
 int mrsb_set_feedforward_velocity_hdg(mrsb_handle h, int64_t n, const int32_t* idx, const double* payload);
 int mrsb_set_feedforward_velocity_hdg_rate(mrsb_handle h, int64_t n, const int32_t* idx, const double* payload);
+/* UavSystemRos::callbackTrackerCmd (src/uav_system_ros.cpp:987-1022): one mrs_msgs::TrackerCommand per UAV
+ * becomes all four feed-forwards — VelocityHdg(v, 0), VelocityHdgRate(v, heading_rate), AccelerationHdg(a, 0),
+ * AccelerationHdgRate(a, heading_rate) — where the parts the message does not "use" are zero.
+ * rows[k][11] = velocity xyz | acceleration xyz | heading_rate | use_velocity_horizontal |
+ * use_velocity_vertical | use_heading_rate | use_acceleration (flags: non-zero = true). */
+#define MRSB_TRACKER_CMD_STRIDE 11
+int mrsb_set_tracker_cmd(mrsb_handle h, int64_t n, const int32_t* idx, const double* rows);
 int mrsb_clear_feedforward(mrsb_handle h, int64_t n, const int32_t* idx);
 
 /* ---- stepping: UavSystem::makeStep(dt) (US:304-380) for every UAV of the batch -------------

@@ -80,6 +80,7 @@ SIGNATURES = {
     "mrsb_set_feedforward_acceleration_hdg": (C.c_int, _N_IDX + [C.c_void_p]),
     "mrsb_set_feedforward_velocity_hdg": (C.c_int, _N_IDX + [C.c_void_p]),
     "mrsb_set_feedforward_velocity_hdg_rate": (C.c_int, _N_IDX + [C.c_void_p]),
+    "mrsb_set_tracker_cmd": (C.c_int, _N_IDX + [C.c_void_p]),
     "mrsb_clear_feedforward": (C.c_int, _N_IDX),
     "mrsb_make_step": (C.c_int, [H, C.c_double, C.c_int32]),
     "mrsb_run": (C.c_int, [H, C.c_double, C.c_int32, C.c_int32, C.c_int32]),

@@ -132,6 +132,14 @@ class UavBatch:
         pl = np.ascontiguousarray(payload, dtype=np.float64).reshape(n, 4)
         check(getattr(self._L, "mrsb_set_feedforward_" + kind)(self.h, n, _ptr(idx), _ptr(pl)))
 
+    def set_tracker_cmd(self, rows, idx=None):
+        """UavSystemRos::callbackTrackerCmd (uav_system_ros.cpp:987-1022): rows [n][11] = velocity xyz, acceleration xyz,
+        heading_rate, use_velocity_horizontal, use_velocity_vertical, use_heading_rate, use_acceleration."""
+        idx = _idx(idx)
+        n = self._n(idx)
+        pl = np.ascontiguousarray(rows, dtype=np.float64).reshape(n, 11)
+        check(self._L.mrsb_set_tracker_cmd(self.h, n, _ptr(idx), _ptr(pl)))
+
     def clear_feedforward(self, idx=None):
         idx = _idx(idx)
         check(self._L.mrsb_clear_feedforward(self.h, self._n(idx), _ptr(idx)))

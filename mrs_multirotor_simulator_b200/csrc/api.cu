@@ -823,6 +823,30 @@ int mrsb_set_feedforward_velocity_hdg_rate(mrsb_handle h, int64_t n, const int32
   GUARD(h);
   return put_rows(h, h->ds.ff, FF_ROWS, FF_VEL_HDG_RATE, 3, n, idx, payload, 4, FLAG_FF_VEL_HDG_RATE);
 }
+int mrsb_set_tracker_cmd(mrsb_handle h, int64_t n, const int32_t* idx, const double* rows) {
+  GUARD(h);
+  if (n < 0 || (n > 0 && !rows)) return fail(MRSB_ERR_INVALID, "null payload");
+  // uav_system_ros.cpp:995-1021
+  std::vector<double> vel_hdg(4 * size_t(n)), vel_hdg_rate(4 * size_t(n)), acc_hdg(4 * size_t(n)), acc_hdg_rate(4 * size_t(n));
+  for (int64_t k = 0; k < n; k++) {
+    const double* r  = rows + MRSB_TRACKER_CMD_STRIDE * k;
+    const bool    uh = r[7] != 0.0, uv = r[8] != 0.0, ur = r[9] != 0.0, ua = r[10] != 0.0;
+    const double  v[3]  = {uh ? r[0] : 0.0, uh ? r[1] : 0.0, uv ? r[2] : 0.0};
+    const double  a[3]  = {ua ? r[3] : 0.0, ua ? r[4] : 0.0, ua ? r[5] : 0.0};
+    const double  rate  = ur ? r[6] : 0.0;
+    for (int c = 0; c < 3; c++) {
+      vel_hdg[4 * k + c] = vel_hdg_rate[4 * k + c] = v[c];
+      acc_hdg[4 * k + c] = acc_hdg_rate[4 * k + c] = a[c];
+    }
+    vel_hdg[4 * k + 3] = acc_hdg[4 * k + 3] = 0.0;
+    vel_hdg_rate[4 * k + 3] = acc_hdg_rate[4 * k + 3] = rate;
+  }
+  int rc = mrsb_set_feedforward_velocity_hdg(h, n, idx, vel_hdg.data());
+  if (!rc) rc = mrsb_set_feedforward_velocity_hdg_rate(h, n, idx, vel_hdg_rate.data());
+  if (!rc) rc = mrsb_set_feedforward_acceleration_hdg(h, n, idx, acc_hdg.data());
+  if (!rc) rc = mrsb_set_feedforward_acceleration_hdg_rate(h, n, idx, acc_hdg_rate.data());
+  return rc;
+}
 int mrsb_clear_feedforward(mrsb_handle h, int64_t n, const int32_t* idx) {
   GUARD(h);
   const int32_t* d_idx = nullptr;

@@ -164,3 +164,37 @@ def test_device_resident_commands_and_state_view():
         assert np.array_equal(tiles[i // v.tile, 15 + c, i % v.tile], sb["omega"][:, c])
     for c in range(9):
         assert np.array_equal(tiles[i // v.tile, 6 + c, i % v.tile], sb["R"][:, c])
+
+
+def test_tracker_cmd_sets_the_four_feedforwards():
+    """UavSystemRos::callbackTrackerCmd (uav_system_ros.cpp:987-1022): mrsb_set_tracker_cmd == the four
+    setFeedforward calls the callback makes, with the unused parts zeroed — against the reference's own code."""
+    from mrs_multirotor_simulator_b200 import UavBatch
+
+    n = 64
+    spawn = grid_spawn(n, z=6.0)
+    rows = np.stack([rand(4, 1, n, -1, 1), rand(4, 2, n, -1, 1), rand(4, 3, n, -0.5, 0.5), rand(4, 4, n, -1, 1), rand(4, 5, n, -1, 1),
+                     rand(4, 6, n, -0.5, 0.5), rand(4, 7, n, -0.5, 0.5), (np.arange(n) % 2).astype(float), (np.arange(n) // 2 % 2).astype(float),
+                     (np.arange(n) // 4 % 2).astype(float), (np.arange(n) // 8 % 2).astype(float)], axis=1)
+    uh, uv, ur, ua = (rows[:, 7 + k] != 0 for k in range(4))
+    v = np.stack([np.where(uh, rows[:, 0], 0.0), np.where(uh, rows[:, 1], 0.0), np.where(uv, rows[:, 2], 0.0)], axis=1)
+    a = np.where(ua[:, None], rows[:, 3:6], 0.0)
+    rate = np.where(ur, rows[:, 6], 0.0)
+    zero = np.zeros(n)
+    gpu = UavBatch([af("x500")], spawn_xyz=spawn, n=n)
+    gpu.set_tracker_cmd(rows)
+    have_ref = O.refsys_lib() is not None
+    ref = (O.RefSwarm if have_ref else O.OracleSwarm)([af("x500")], spawn_xyz=spawn, n=n)
+    ref.set_feedforward(2, np.column_stack([v, zero]))   # VelocityHdg(velocity, 0)
+    ref.set_feedforward(3, np.column_stack([v, rate]))   # VelocityHdgRate(velocity, heading_rate)
+    ref.set_feedforward(1, np.column_stack([a, zero]))   # AccelerationHdg(acceleration, 0)
+    ref.set_feedforward(0, np.column_stack([a, rate]))   # AccelerationHdgRate(acceleration, heading_rate)
+    for mode in (O.POSITION_CMD, O.VELOCITY_HDG_RATE_CMD, O.VELOCITY_HDG_CMD):
+        cmd = np.stack([spawn[:, 0] + 1.0, spawn[:, 1] - 1.0, np.full(n, 7.0), rand(4, 9, n, -1, 1)], axis=1) if mode == O.POSITION_CMD else \
+            np.stack([rand(4, 10, n, -1, 1), rand(4, 11, n, -1, 1), rand(4, 12, n, -0.5, 0.5), rand(4, 13, n, -1, 1)], axis=1)
+        for s in (ref, gpu):
+            s.set_input(mode, cmd)
+        ref.make_step(0.01, 150)
+        for _ in range(150):
+            gpu.make_step(0.01)
+        assert_parity(ref, gpu, what=f"tracker feed-forwards, mode {mode}")
