@@ -295,6 +295,11 @@ int mrsb_set_pair_capacity(mrsb_handle h, int64_t max_pairs);
 /* Cumulative counters since create: [0] steps, [1] collision passes, [2] directed pairs emitted
  * by the last pass, [3] crashed UAVs in this shard, [4] kernels launched by this handle. */
 int mrsb_get_counters(mrsb_handle h, int64_t* out5);
+/* Which stepping kernel the LAST mrsb_make_step launched (diagnostics; results do not depend on it — every variant
+ * computes the same bits): [0] 0 = none yet, 1 = direct (one CTA per 128-UAV tile reading HBM), 2 = staged (persistent
+ * CTAs, next tile fetched by TMA bulk copies into shared memory); [1] grid size; [2] motors per UAV the kernel was
+ * specialised for (0 = per UAV); [3] INPUT_MODE it was specialised for (-1 = per UAV). */
+int mrsb_get_step_info(mrsb_handle h, int32_t* out4);
 /* How the collision pass (SIM:295-359) is organised on this handle: [0] cell edge of the spatial hash in
  * metres, [1] 1 if neighbour lists are kept between table rebuilds (single-shard handles), [2] list
  * radius, [3] skin (the lists survive while twice the accumulated displacement bound stays below it),

@@ -329,6 +329,13 @@ class UavBatch:
         check(self._L.mrsb_get_counters(self.h, _ptr(out)))
         return dict(steps=int(out[0]), collision_passes=int(out[1]), pairs=int(out[2]), crashed=int(out[3]), launches=int(out[4]))
 
+    def step_info(self):
+        """Which stepping kernel the last make_step launched (diagnostics): variant 'direct' | 'staged', grid, motors, mode."""
+        out = np.zeros(4, dtype=np.int32)
+        check(self._L.mrsb_get_step_info(self.h, _ptr(out)))
+        return dict(variant={0: "none", 1: "direct", 2: "staged", 3: "staged+peer-stores"}[int(out[0])], grid=int(out[1]), n_motors=int(out[2]),
+                    mode=int(out[3]))
+
     def collision_info(self):
         """How the collision pass is organised on this handle (diagnostics; results do not depend on it)."""
         out = np.zeros(8, dtype=np.float64)

@@ -162,6 +162,7 @@ struct mrsb_sim {
   uint32_t* h_one              = nullptr;  // pinned constant 1 (source of the async "force rebuild" copy)
 
   int64_t n_steps = 0, n_passes = 0, n_launches = 0;
+  int     step_info[4] = {0, 0, 0, 0};  // last stepping launch: variant, grid, NM_T, MODE_T (mrsb_get_step_info)
 };
 
 static void drop_collision_graphs(mrsb_sim* h) {
@@ -994,7 +995,7 @@ int mrsb_make_step(mrsb_handle h, double dt, int32_t k_substeps) {
     h->pushed = true;
   }
   h->n_launches += launch_step(h->ds, h->uniform_pset >= 0 ? &h->uniform_params : nullptr, dt, k_substeps, h->uniform_mode, h->uniform_nm,
-                               h->any_moment, h->stream);
+                               h->any_moment, h->stream, h->step_info);
   h->n_steps += k_substeps;
   h->steps_since_pass++;
   CU(cudaGetLastError());
@@ -1454,6 +1455,13 @@ int mrsb_get_counters(mrsb_handle h, int64_t* out5) {
   out5[2] = int64_t(found);
   out5[3] = crashed;
   out5[4] = h->n_launches;
+  return MRSB_OK;
+}
+
+int mrsb_get_step_info(mrsb_handle h, int32_t* out4) {
+  GUARD(h);
+  if (!out4) return fail(MRSB_ERR_INVALID, "null output");
+  for (int k = 0; k < 4; k++) out4[k] = h->step_info[k];
   return MRSB_OK;
 }
 

@@ -137,8 +137,10 @@ struct DevGrid {
 
 // kernel launchers (step_kernel.cu / collide.cu / io_kernels.cu); all return the number of launches made
 // uniform_params: host copy of THE parameter set when every local UAV uses the same one, else nullptr
+// info[4] (may be nullptr): [0] variant launched — 1 direct (one CTA per tile), 2 staged (persistent CTAs + TMA); [1] grid;
+// [2] NM_T and [3] MODE_T of the instantiation
 int launch_step(const DevState& s, const DevParams* uniform_params, double dt, int k_substeps, int uniform_mode, int uniform_nm, bool any_moment,
-                cudaStream_t stream);
+                cudaStream_t stream, int* info);
 int launch_collide(const DevState& s, const DevGrid& g, int crash_mode, double rebounce, void* cub_tmp, size_t cub_tmp_bytes, cudaStream_t stream);
 // the pass with neighbour lists: decide (always) | rebuild (body of the graph's conditional node) | check (always)
 int launch_collide_decide(const DevGrid& g, int always, cudaGraphConditionalHandle handle, int has_handle, cudaStream_t stream);

@@ -923,9 +923,11 @@ int staged_grid(size_t smem) {
 }
 
 template <int NM_T, int MODE_T>
-void launch_one(const DevState& s, const DevParams* uniform_params, double dt, int k, int any_moment, cudaStream_t st) {
+void launch_one(const DevState& s, const DevParams* uniform_params, double dt, int k, int any_moment, cudaStream_t st, int* info) {
   const int     threads = MRSB_STEP_THREADS;
   const int64_t n_tiles = (s.n + threads - 1) / threads;
+  info[2] = NM_T;
+  info[3] = MODE_T;
   if constexpr (NM_T > 0 && MODE_T >= 0) if (uniform_params) {
     // enough tiles to fill the machine more than once: persistent CTAs + TMA staging hide the HBM
     // latency behind the integration of the previous tile
@@ -936,6 +938,8 @@ void launch_one(const DevState& s, const DevParams* uniform_params, double dt, i
       const int      grid = staged_grid<NM_T, MODE_T, kOne, kBulk>(smem);
       if (grid <= 0 || n_tiles <= grid) return false;
       uav_step_staged_kernel<NM_T, MODE_T, kOne, kBulk><<<grid, threads, smem, st>>>(s, *uniform_params, dt, k, any_moment, n_tiles);
+      info[0] = kBulk ? 3 : 2;
+      info[1] = grid;
       return true;
     };
     if (!getenv("MRSB_NO_STAGING")) {
@@ -946,6 +950,8 @@ void launch_one(const DevState& s, const DevParams* uniform_params, double dt, i
       if (done) return;
     }
   }
+  info[0] = 1;
+  info[1] = int(n_tiles);
   if (k == 1) {
     uav_step_kernel<NM_T, MODE_T, true><<<unsigned(n_tiles), threads, 0, st>>>(s, dt, k, any_moment);
   } else {
@@ -954,22 +960,22 @@ void launch_one(const DevState& s, const DevParams* uniform_params, double dt, i
 }
 
 template <int NM_T>
-void launch_nm(const DevState& s, const DevParams* up, double dt, int k, int mode, int any_moment, cudaStream_t st) {
+void launch_nm(const DevState& s, const DevParams* up, double dt, int k, int mode, int any_moment, cudaStream_t st, int* info) {
   switch (mode) {
     case MRSB_ACTUATOR_CMD:
-      launch_one<NM_T, MRSB_ACTUATOR_CMD>(s, up, dt, k, any_moment, st);
+      launch_one<NM_T, MRSB_ACTUATOR_CMD>(s, up, dt, k, any_moment, st, info);
       break;
     case MRSB_VELOCITY_HDG_RATE_CMD:
-      launch_one<NM_T, MRSB_VELOCITY_HDG_RATE_CMD>(s, up, dt, k, any_moment, st);
+      launch_one<NM_T, MRSB_VELOCITY_HDG_RATE_CMD>(s, up, dt, k, any_moment, st, info);
       break;
     case MRSB_VELOCITY_HDG_CMD:
-      launch_one<NM_T, MRSB_VELOCITY_HDG_CMD>(s, up, dt, k, any_moment, st);
+      launch_one<NM_T, MRSB_VELOCITY_HDG_CMD>(s, up, dt, k, any_moment, st, info);
       break;
     case MRSB_POSITION_CMD:
-      launch_one<NM_T, MRSB_POSITION_CMD>(s, up, dt, k, any_moment, st);
+      launch_one<NM_T, MRSB_POSITION_CMD>(s, up, dt, k, any_moment, st, info);
       break;
     default:
-      launch_one<NM_T, -1>(s, up, dt, k, any_moment, st);
+      launch_one<NM_T, -1>(s, up, dt, k, any_moment, st, info);
       break;
   }
 }
@@ -979,6 +985,7 @@ void launch_nm(const DevState& s, const DevParams* up, double dt, int k, int mod
 // one translation unit per motor count (step_kernel_nm{0,4,6,8}.cu) instantiates this, so that the
 // ~40 kernel instantiations compile in parallel
 template <int NM_T>
-void launch_step_nm(const DevState& s, const DevParams* uniform_params, double dt, int k_substeps, int uniform_mode, bool any_moment, cudaStream_t stream) {
-  launch_nm<NM_T>(s, uniform_params, dt, k_substeps, uniform_mode, any_moment, stream);
+void launch_step_nm(const DevState& s, const DevParams* uniform_params, double dt, int k_substeps, int uniform_mode, bool any_moment, cudaStream_t stream,
+                    int* info) {
+  launch_nm<NM_T>(s, uniform_params, dt, k_substeps, uniform_mode, any_moment, stream, info);
 }
