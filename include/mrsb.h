@@ -214,9 +214,26 @@ int mrsb_clear_feedforward(mrsb_handle h, int64_t n, const int32_t* idx);
 int mrsb_make_step(mrsb_handle h, double dt, int32_t k_substeps);
 
 /* One tick of the reference node's loop (SIM:198-231): makeStep for all, then handleCollisions;
- * repeated n_ticks times without host synchronisation.  In a sharded job every rank must call
- * it with the same arguments (the collision pass contains the position all-gather). */
+ * repeated n_ticks times without host synchronisation (with neighbour lists each tick is ONE CUDA
+ * graph launch: stepping kernel + collision pass).  In a sharded job every rank must call it with
+ * the same arguments (the collision pass contains the cross-shard exchange). */
 int mrsb_run(mrsb_handle h, double dt, int32_t k_substeps, int32_t n_ticks, int32_t with_collisions);
+
+/* UavSystemRos::makeStep (ROSW:242-271) steps a UAV only `if (_iterate_without_input_ || time_last_input_ > 0)`
+ * (ROSW:265; parameter `iterate_without_input`, config/multirotor_simulator.yaml:10, default true).  With enabled = 0 a
+ * UAV that has not received a command yet (any mrsb_set_input* with a payload), or whose input timed out
+ * (mrsb_timeout_input resets time_last_input_, ROSW:256-259), is left untouched by mrsb_make_step: state, PIDs, IMU and
+ * flags keep their values. */
+int mrsb_set_iterate_without_input(mrsb_handle h, int32_t enabled);
+
+/* Which optional per-UAV rows mrsb_make_step stores (default: all).  The fabricated accelerometer (MM:280-281) and the packed
+ * positions cost 24 bytes per UAV-step each; a caller that never reads them (RL loops reading state through the device view)
+ * switches them off.  With MRSB_OUT_IMU off, mrsb_get_imu_acceleration / mrsb_get_imu / mrsb_pack_observations_device fail with
+ * MRSB_ERR_STATE instead of returning stale values.  The library keeps storing positions whenever the collision pass or a
+ * peer shard needs them, whatever the mask says. */
+#define MRSB_OUT_IMU 1u
+#define MRSB_OUT_POSITIONS 2u
+int mrsb_set_outputs(mrsb_handle h, uint32_t mask);
 
 /* ---- state: UavSystem::getState (US:386-390, MM:90-98), getImuAcceleration (US:424-427) ----
  * any output pointer may be NULL.  Rows: x[3] v[3] R[9 col-major] omega[3] motor_rpm[MRSB_MAX_MOTORS]. */
@@ -318,11 +335,18 @@ int mrsb_get_collision_info(mrsb_handle h, double* out8);
  *      (this shard's slice, filled by mrsb_publish_positions, starts at shard_begin*3).        */
 int mrsb_nccl_unique_id(void* out128);
 int mrsb_comm_init_nccl(mrsb_handle h, int32_t n_ranks, int32_t rank, const void* unique_id128);
-/* How mrsb_handle_collisions exchanges positions: 0 = single shard, 1 = NCCL all-gather,
- * 2 = fused: peers mapped over CUDA IPC at mrsb_comm_init_nccl, the stepping kernel stores every
- * position into all peers' buffers over NVLink and the collision pass only hand-shakes
- * (set MRSB_NO_P2P=1 to force mode 1).  In sharded runs every rank must issue the same sequence
- * of mrsb_make_step / position-writing calls, as with any collective. */
+/* How mrsb_handle_collisions exchanges positions: 0 = single shard, 1 = NCCL all-gather of the
+ * whole swarm every pass, 2 = pull over peer memory: every rank's position buffer (plus one bounding
+ * box per 32 UAVs and the collision geometry) is mapped into its peers over CUDA IPC at
+ * mrsb_comm_init_nccl; nothing is copied per tick — the pass' first kernel hand-shakes with the
+ * peers, then reads exactly the remote positions it needs over NVLink (the candidates in its
+ * neighbour lists; at a table rebuild the halo around its bounding box).  MRSB_NO_P2P=1 forces
+ * mode 1.  In sharded runs every rank must issue the same sequence of mrsb_handle_collisions /
+ * mrsb_run calls, as with any collective; any number of mrsb_make_step or state-writing calls may
+ * lie between two passes.  Per-UAV model parameters that the collision pass of OTHER shards reads
+ * (arm length, propeller radius, mass: mrsb_set_params, mrsb_set_mass) can be changed in mode 2
+ * (peers read the owner's values) or on unsharded handles; in modes 0/1 of a sharded handle such a
+ * call fails with MRSB_ERR_STATE. */
 int mrsb_exchange_mode(mrsb_handle h);
 int mrsb_gather_buffer(mrsb_handle h, void** device_ptr, size_t* bytes);
 int mrsb_publish_positions(mrsb_handle h);

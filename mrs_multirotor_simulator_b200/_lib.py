@@ -84,6 +84,8 @@ SIGNATURES = {
     "mrsb_clear_feedforward": (C.c_int, _N_IDX),
     "mrsb_make_step": (C.c_int, [H, C.c_double, C.c_int32]),
     "mrsb_run": (C.c_int, [H, C.c_double, C.c_int32, C.c_int32, C.c_int32]),
+    "mrsb_set_iterate_without_input": (C.c_int, [H, C.c_int32]),
+    "mrsb_set_outputs": (C.c_int, [H, C.c_uint32]),
     "mrsb_get_state": (C.c_int, _N_IDX + [C.c_void_p] * 5),
     "mrsb_get_v_prev": (C.c_int, _N_IDX + [C.c_void_p]),
     "mrsb_get_imu_acceleration": (C.c_int, _N_IDX + [C.c_void_p]),

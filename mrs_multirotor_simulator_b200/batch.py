@@ -151,6 +151,14 @@ class UavBatch:
     def run(self, dt, n_ticks, k_substeps=1, with_collisions=True):
         check(self._L.mrsb_run(self.h, float(dt), int(k_substeps), int(n_ticks), int(bool(with_collisions))))
 
+    def set_iterate_without_input(self, enabled):
+        """`iterate_without_input` of the reference (uav_system_ros.cpp:265): with False, UAVs without a command are not stepped."""
+        check(self._L.mrsb_set_iterate_without_input(self.h, int(bool(enabled))))
+
+    def set_outputs(self, imu=True, positions=True):
+        """Which optional rows make_step stores: the fabricated accelerometer (multirotor_model.hpp:280-281) and the packed positions."""
+        check(self._L.mrsb_set_outputs(self.h, (1 if imu else 0) | (2 if positions else 0)))
+
     def sync(self):
         check(self._L.mrsb_sync(self.h))
 

@@ -117,25 +117,34 @@ struct mrsb_sim {
 
   int    coll_enabled = 0, coll_crash = 0;
   double coll_rebounce = 0.0;
-  void*  cub_tmp       = nullptr;
-  size_t cub_tmp_bytes = 0;
+
+  double   filt_dt  = -1.0;   // dt the DevParams::filt column of the device table was last prepared for (< 0: stale)
+  uint32_t outputs  = MRSB_OUT_IMU | MRSB_OUT_POSITIONS;  // mrsb_set_outputs
+  bool     iterate_without_input = true;                  // mrsb_set_iterate_without_input (ROSW:265)
+  double*  d_geom[2] = {nullptr, nullptr};                // collision geometry [n_global][4]; [1] only with the pull exchange
 
   ncclComm_t           comm    = nullptr;
   int                  n_ranks = 1, rank = 0;
   std::vector<int64_t> shard_begin_of, shard_count_of;
   bool                 equal_shards = true;
 
-  // fused position exchange over peer memory (set up by mrsb_comm_init_nccl when every peer is reachable)
+  // Pull exchange over peer memory (set up by mrsb_comm_init_nccl when every peer is reachable).  Positions, per-group boxes
+  // and collision geometry exist twice; collision pass number k (1, 2, ...) READS buffer k & 1 on every rank, and everything
+  // that writes positions between pass k - 1 and pass k writes buffer k & 1 — a peer that is still inside pass k - 1 reads the
+  // other one, and it cannot be further behind than that (the hand-shake of pass k waits for it).
   bool                 p2p       = false;
-  double*              gbuf[2]   = {nullptr, nullptr};  // double-buffered gather buffer (parity flips every step)
-  int                  parity    = 0;
-  bool                 pushed    = false;  // the current buffer was last written by a pushing step kernel
-  unsigned long long   epoch     = 0;
-  double**             d_peers[2] = {nullptr, nullptr};  // device arrays [n_ranks] of the peers' gbuf[parity]
-  unsigned long long*  d_flags   = nullptr;              // [n_ranks] written by the peers
-  unsigned long long** d_peer_flags = nullptr;           // device array [n_ranks] of the peers' d_flags
+  double*              gbuf[2]   = {nullptr, nullptr};
+  uint32_t*            d_gbox[2] = {nullptr, nullptr};
+  int64_t              pass_no   = 0;      // collision passes done so far (pull exchange)
+  bool                 wrote_since_pass = false;  // positions of buffer (pass_no + 1) & 1 are complete
+  std::vector<int32_t> pending_geom[2];    // local indices whose geometry changed but is not yet in that buffer (-1 = all)
+  PeerView             pv[2]{};            // what the kernels of a pass with parity k read
+  PeerView             pv_local{};         // everything in this handle's own arrays
+  P2PCtl               p2pctl{};
+  unsigned long long*  d_flags   = nullptr;              // this rank's flag block, written by the peers
+  unsigned long long** d_peer_flags = nullptr;           // device array [n_ranks] of the peers' flag blocks
   std::vector<void*>   ipc_opened;
-  int*                 h_status  = nullptr;              // pinned, mapped: set by the wait kernel on time-out
+  int*                 h_status  = nullptr;              // pinned, mapped: set by the hand-shake on time-out
 
   // pipelined host I/O (mrsb_set_input_async / mrsb_get_positions_async)
   cudaStream_t up_stream = nullptr, down_stream = nullptr;
@@ -160,6 +169,11 @@ struct mrsb_sim {
   bool     list_graph_failed   = false; // conditional graph nodes unavailable: do not try again on every pass
   int64_t  rebuilds_counted    = 0;
   uint32_t* h_one              = nullptr;  // pinned constant 1 (source of the async "force rebuild" copy)
+  cudaGraphExec_t tick_graph[2] = {nullptr, nullptr};  // mrsb_run: stepping launch + collision pass as ONE graph per parity
+  double   tick_dt = 0.0;
+  int      tick_k = 0, tick_mode = -2, tick_nm = -1, tick_pset = -2, tick_own[2] = {0, 0};
+  uint32_t tick_opts = 0;
+  bool     tick_failed = false;
 
   int64_t n_steps = 0, n_passes = 0, n_launches = 0;
   int     step_info[4] = {0, 0, 0, 0};  // last stepping launch: variant, grid, NM_T, MODE_T (mrsb_get_step_info)
@@ -169,6 +183,8 @@ static void drop_collision_graphs(mrsb_sim* h) {
   for (int k = 0; k < 2; k++) {
     if (h->coll_graph[k]) cudaGraphExecDestroy(h->coll_graph[k]);
     h->coll_graph[k] = nullptr;
+    if (h->tick_graph[k]) cudaGraphExecDestroy(h->tick_graph[k]);
+    h->tick_graph[k] = nullptr;
   }
 }
 
@@ -213,9 +229,39 @@ static ParamSet canonical(const mrsb_model_params& mp, const mrsb_controller_par
   return s;
 }
 
+// Parameter sets nobody refers to any more (per-UAV edits intern a new set per distinct value): dropped once they are the
+// majority, ids renumbered, the whole per-UAV index table uploaded again.
+static int collect_param_sets(mrsb_sim* h) {
+  const int n_sets = int(h->sets.size());
+  if (n_sets <= 32) return MRSB_OK;
+  std::vector<int> refs(size_t(n_sets), 0);
+  for (int32_t id : h->pset_host) refs[size_t(id)]++;
+  int live = 0;
+  for (int r : refs) live += r > 0;
+  if (2 * live > n_sets) return MRSB_OK;
+  std::vector<int>      remap(size_t(n_sets), -1);
+  std::vector<ParamSet> kept;
+  kept.reserve(size_t(live));
+  h->set_index.clear();
+  for (int k = 0; k < n_sets; k++) {
+    if (!refs[size_t(k)]) continue;
+    remap[size_t(k)] = int(kept.size());
+    h->set_index[set_key(h->sets[size_t(k)])] = int(kept.size());
+    kept.push_back(h->sets[size_t(k)]);
+  }
+  h->sets.swap(kept);
+  h->tick_pset = -2;  // ids mean something else now
+  for (int32_t& id : h->pset_host) id = remap[size_t(id)];
+  CU(cudaMemcpyAsync(h->d_pset, h->pset_host.data(), sizeof(int32_t) * h->pset_host.size(), cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return MRSB_OK;
+}
+
 // upload the parameter table if it changed; recompute the launch specialisation hints
 static int flush_params(mrsb_sim* h) {
   if (!h->params_dirty) return MRSB_OK;
+  int rc = collect_param_sets(h);
+  if (rc) return rc;
   const int n_sets = int(h->sets.size());
   if (n_sets > h->d_params_cap) {
     CU(cudaStreamSynchronize(h->stream));
@@ -229,6 +275,7 @@ static int flush_params(mrsb_sim* h) {
   for (int k = 0; k < n_sets; k++) mrsb_derive(h->sets[k].mp, h->sets[k].cp, &host[k]);
   CU(cudaMemcpyAsync(h->d_params, host.data(), sizeof(DevParams) * n_sets, cudaMemcpyHostToDevice, h->stream));
   CU(cudaStreamSynchronize(h->stream));  // `host` goes out of scope
+  h->filt_dt = -1.0;                     // DevParams::filt has to be prepared again (ensure_filt)
   int nm = -1, ps = -2;
   for (int64_t i = 0; i < h->ds.n; i++) {
     const int id = h->pset_host[h->ds.shard_begin + i];
@@ -243,6 +290,22 @@ static int flush_params(mrsb_sim* h) {
   h->uniform_pset = ps >= 0 ? ps : -1;
   if (h->uniform_pset >= 0) h->uniform_params = host[size_t(h->uniform_pset)];
   h->params_dirty = false;
+  return MRSB_OK;
+}
+
+// DevParams::filt = exp(-dt / tau) for every set, evaluated on the device (the same bits whichever kernel variant reads them);
+// the staged kernel takes the batch's one set by value, so its host copy gets the device's result.
+static int ensure_filt(mrsb_sim* h, double dt) {
+  if (h->filt_dt == dt) return MRSB_OK;
+  h->n_launches += launch_prep_params(h->d_params, int(h->sets.size()), dt, h->stream);
+  if (h->uniform_pset >= 0)
+    CU(cudaMemcpyAsync(&h->uniform_params.filt, &h->d_params[h->uniform_pset].filt, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  h->filt_dt = dt;
+  for (int k = 0; k < 2; k++) {  // the tick graphs hold the parameter set by value
+    if (h->tick_graph[k]) cudaGraphExecDestroy(h->tick_graph[k]);
+    h->tick_graph[k] = nullptr;
+  }
   return MRSB_OK;
 }
 
@@ -309,30 +372,86 @@ static int stride_of(int mode) {
   }
 }
 
-// re-point the addressed UAVs to (possibly new) parameter sets produced by `edit`
-template <class Edit>
-static int repoint(mrsb_sim* h, int64_t n, const int32_t* idx, Edit edit) {
+// ---- collision geometry (arm, propeller radius, mass per UAV): what the collision pass reads of the parameters ----------
+// which buffer position / geometry writes go to right now
+static int write_buf(const mrsb_sim* h) {
+  return h->p2p ? int((h->pass_no + 1) & 1) : 0;
+}
+// geometry of the addressed local UAVs (idx == nullptr: all of them) from the device tables into buffer `b`
+static int apply_geom(mrsb_sim* h, int b, int64_t n, const int32_t* d_idx) {
+  h->n_launches += launch_set_geom(h->d_geom[b], n, d_idx, h->ds.shard_begin, h->d_pset, h->d_params, h->stream);
+  CU(cudaGetLastError());
+  return MRSB_OK;
+}
+// Geometry of local UAVs changed (d_idx: their local indices on the device, nullptr = all).  The buffer being written gets it now;
+// with the pull exchange the other buffer may still be read by a peer that is one pass behind, so it gets it when it becomes
+// the write buffer (apply_pending_geom, after the next pass).
+static int geometry_changed(mrsb_sim* h, int64_t n, const int32_t* idx, const int32_t* d_idx) {
+  const int w  = write_buf(h);
+  int       rc = apply_geom(h, w, n, d_idx);
+  if (rc || !h->p2p) return rc;
+  std::vector<int32_t>& pend = h->pending_geom[w ^ 1];
+  if (!idx || (pend.size() == 1 && pend[0] < 0)) {
+    pend.assign(1, -1);
+  } else {
+    pend.insert(pend.end(), idx, idx + n);
+  }
+  return MRSB_OK;
+}
+static int stage_idx(mrsb_sim* h, int64_t n, const int32_t* idx, const int32_t** out);
+static int apply_pending_geom(mrsb_sim* h, int b) {
+  std::vector<int32_t>& pend = h->pending_geom[b];
+  if (pend.empty()) return MRSB_OK;
+  int rc;
+  if (pend[0] < 0) {
+    rc = apply_geom(h, b, h->ds.n, nullptr);
+  } else {
+    const int32_t* d_idx = nullptr;
+    rc                   = stage_idx(h, int64_t(pend.size()), pend.data(), &d_idx);
+    if (!rc) rc = apply_geom(h, b, int64_t(pend.size()), d_idx);
+    if (!rc) CU(cudaStreamSynchronize(h->stream));
+  }
+  pend.clear();
+  return rc;
+}
+
+// re-point the addressed UAVs to (possibly new) parameter sets produced by `edit(set, k)`; `value_key(k)` tells edits with the
+// same outcome apart from others (UAVs with the same old set and the same 64-bit key share the new set)
+template <class Edit, class Key>
+static int repoint(mrsb_sim* h, int64_t n, const int32_t* idx, Edit edit, Key value_key) {
   const int32_t* d_idx = nullptr;
   int            rc    = stage_idx(h, n, idx, &d_idx);
   if (rc) return rc;
   if (n == 0) return MRSB_OK;
-  std::vector<int32_t> ids(static_cast<size_t>(n), 0);
-  std::map<int, int>   memo;
+  std::vector<int32_t>                 ids(static_cast<size_t>(n), 0), olds(static_cast<size_t>(n), 0);
+  std::map<std::pair<int, uint64_t>, int> memo;
+  bool geometry = false;
   for (int64_t k = 0; k < n; k++) {
     const int64_t i   = idx ? idx[k] : k;
     const int     old = h->pset_host[size_t(h->ds.shard_begin + i)];
-    auto          it  = memo.find(old);
+    olds[size_t(k)]   = old;
+    const auto    key = std::make_pair(old, uint64_t(value_key(k)));
+    auto          it  = memo.find(key);
     int           id;
     if (it != memo.end()) {
       id = it->second;
     } else {
       ParamSet s = h->sets[old];
-      edit(s);
+      edit(s, k);
       id        = intern_set(h, canonical(s.mp, s.cp));
-      memo[old] = id;
+      memo[key] = id;
+      const mrsb_model_params &a = h->sets[size_t(old)].mp, &b = h->sets[size_t(id)].mp;
+      if (a.arm_length != b.arm_length || a.prop_radius != b.prop_radius || a.mass != b.mass) geometry = true;
     }
     ids[size_t(k)]                                 = id;
     h->pset_host[size_t(h->ds.shard_begin + i)] = id;
+  }
+  if (geometry && h->ds.n_global > h->ds.n && !h->p2p) {
+    // the collision pass of the OTHER shards evaluates arm + prop and the rebounce weight of these UAVs (SIM:342,350); only the
+    // pull exchange lets them read the owner's values
+    for (int64_t k = n - 1; k >= 0; k--) h->pset_host[size_t(h->ds.shard_begin + (idx ? idx[k] : k))] = olds[size_t(k)];  // nothing changed
+    return fail(MRSB_ERR_STATE, "arm length / propeller radius / mass of a sharded handle can only change while its peers read them from this "
+                                "GPU (exchange mode 2, mrsb_comm_init_nccl with peer access)");
   }
   h->params_dirty = true;
   rc              = ensure_stage(h, sizeof(int32_t) * size_t(n));
@@ -340,11 +459,18 @@ static int repoint(mrsb_sim* h, int64_t n, const int32_t* idx, Edit edit) {
   CU(cudaMemcpyAsync(h->d_stage, ids.data(), sizeof(int32_t) * size_t(n), cudaMemcpyHostToDevice, h->stream));
   h->n_launches += launch_set_pset(h->d_pset, n, d_idx, h->ds.shard_begin, reinterpret_cast<const int32_t*>(h->d_stage), h->stream);
   CU(cudaStreamSynchronize(h->stream));  // `ids` goes out of scope
+  if (geometry) {
+    rc = flush_params(h);  // the new sets have to be on the device before the geometry is derived from them
+    if (rc) return rc;
+    rc = stage_idx(h, n, idx, &d_idx);
+    if (rc) return rc;
+    rc = geometry_changed(h, n, idx, d_idx);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(h->stream));
+  }
   return MRSB_OK;
 }
 
-// Fused exchange set-up: a second gather buffer, this rank's flag slots, and IPC mappings of every
-// peer's two buffers and flags (handles travel through one NCCL all-gather of raw bytes).
 // Cell geometry of the spatial hash.  Handles that run the full pass every tick use the smallest cell
 // whose half covers the search radius sqrt(3) (4 m: fewest candidates).  Handles that keep neighbour
 // lists between rebuilds use a larger cell: the list radius is just under cell / 2, so a larger cell
@@ -363,22 +489,46 @@ static void set_collision_geometry(mrsb_sim* h, bool lists) {
   h->positions_touched = true;
 }
 
+static void make_local_view(mrsb_sim* h) {
+  PeerView& v = h->pv_local;
+  v           = PeerView{};
+  v.n_ranks   = 1;
+  v.rank      = 0;
+  v.begin[0]  = 0;
+  v.begin[1]  = h->ds.n_global;
+  v.pos[0]    = h->ds.gpos;
+  v.geom[0]   = h->d_geom[0];
+}
+
+// Pull exchange set-up: second copies of the position buffer and the geometry table, per-group boxes, this rank's flag block, and
+// IPC mappings of every peer's (handles travel through one NCCL all-gather of raw bytes).
 static int setup_p2p(mrsb_sim* h) {
   const int    G     = h->n_ranks;
   const size_t bytes = sizeof(double) * 3 * size_t(h->ds.n_global);
-  h->gbuf[0]         = h->ds.gpos;
+  const size_t gbytes = sizeof(double) * 4 * size_t(h->ds.n_global);
+  const size_t bbytes = sizeof(uint32_t) * 6 * size_t(h->ds.ld / 32);
+  h->gbuf[0]          = h->ds.gpos;
   CU(cudaMalloc(&h->gbuf[1], std::max<size_t>(bytes, 16)));
   CU(cudaMemcpy(h->gbuf[1], h->gbuf[0], bytes, cudaMemcpyDeviceToDevice));
-  CU(cudaMalloc(&h->d_flags, sizeof(unsigned long long) * 3 * G));  // epochs [G] + displacement words [2G] (step_kernel.cu)
+  CU(cudaMalloc(&h->d_geom[1], std::max<size_t>(gbytes, 32)));
+  CU(cudaMemcpy(h->d_geom[1], h->d_geom[0], gbytes, cudaMemcpyDeviceToDevice));
+  for (int k = 0; k < 2; k++) {
+    CU(cudaMalloc(&h->d_gbox[k], std::max<size_t>(bbytes, 32)));
+    CU(cudaMemset(h->d_gbox[k], 0, std::max<size_t>(bbytes, 32)));
+  }
+  CU(cudaMalloc(&h->d_flags, sizeof(unsigned long long) * 3 * G));  // pass numbers [G] + displacement words [2G]
   CU(cudaMemset(h->d_flags, 0, sizeof(unsigned long long) * 3 * G));
   CU(cudaHostAlloc(&h->h_status, sizeof(int), cudaHostAllocMapped));
   *h->h_status = 0;
   struct Handles {
-    cudaIpcMemHandle_t buf[2], flags;
+    cudaIpcMemHandle_t buf[2], box[2], geom[2], flags;
   };
   Handles mine;
-  CU(cudaIpcGetMemHandle(&mine.buf[0], h->gbuf[0]));
-  CU(cudaIpcGetMemHandle(&mine.buf[1], h->gbuf[1]));
+  for (int k = 0; k < 2; k++) {
+    CU(cudaIpcGetMemHandle(&mine.buf[k], h->gbuf[k]));
+    CU(cudaIpcGetMemHandle(&mine.box[k], h->d_gbox[k]));
+    CU(cudaIpcGetMemHandle(&mine.geom[k], h->d_geom[k]));
+  }
   CU(cudaIpcGetMemHandle(&mine.flags, h->d_flags));
   Handles* d_all = nullptr;
   CU(cudaMalloc(&d_all, sizeof(Handles) * G));
@@ -389,44 +539,76 @@ static int setup_p2p(mrsb_sim* h) {
   CU(cudaMemcpyAsync(all.data(), d_all, sizeof(Handles) * G, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   CU(cudaFree(d_all));
-  std::vector<double*>             peers0(static_cast<size_t>(G), nullptr), peers1(static_cast<size_t>(G), nullptr);
   std::vector<unsigned long long*> pflags(static_cast<size_t>(G), nullptr);
+  for (int k = 0; k < 2; k++) {
+    PeerView& v = h->pv[k];
+    v           = PeerView{};
+    v.n_ranks   = G;
+    v.rank      = h->rank;
+    for (int r = 0; r < G; r++) v.begin[r] = h->shard_begin_of[size_t(r)];
+    v.begin[G] = h->ds.n_global;
+  }
+  auto open = [&](const cudaIpcMemHandle_t& hd, void** out) -> int {
+    CU(cudaIpcOpenMemHandle(out, hd, cudaIpcMemLazyEnablePeerAccess));
+    h->ipc_opened.push_back(*out);
+    return MRSB_OK;
+  };
   for (int r = 0; r < G; r++) {
     if (r == h->rank) {
-      peers0[size_t(r)] = h->gbuf[0];
-      peers1[size_t(r)] = h->gbuf[1];
+      for (int k = 0; k < 2; k++) {
+        h->pv[k].pos[r]  = h->gbuf[k];
+        h->pv[k].box[r]  = h->d_gbox[k];
+        h->pv[k].geom[r] = h->d_geom[k];
+      }
       pflags[size_t(r)] = h->d_flags;
       continue;
     }
     void* p = nullptr;
-    CU(cudaIpcOpenMemHandle(&p, all[size_t(r)].buf[0], cudaIpcMemLazyEnablePeerAccess));
-    h->ipc_opened.push_back(p);
-    peers0[size_t(r)] = static_cast<double*>(p);
-    CU(cudaIpcOpenMemHandle(&p, all[size_t(r)].buf[1], cudaIpcMemLazyEnablePeerAccess));
-    h->ipc_opened.push_back(p);
-    peers1[size_t(r)] = static_cast<double*>(p);
-    CU(cudaIpcOpenMemHandle(&p, all[size_t(r)].flags, cudaIpcMemLazyEnablePeerAccess));
-    h->ipc_opened.push_back(p);
+    for (int k = 0; k < 2; k++) {
+      int rc = open(all[size_t(r)].buf[k], &p);
+      if (rc) return rc;
+      h->pv[k].pos[r] = static_cast<const double*>(p);
+      rc              = open(all[size_t(r)].box[k], &p);
+      if (rc) return rc;
+      h->pv[k].box[r] = static_cast<const uint32_t*>(p);
+      rc              = open(all[size_t(r)].geom[k], &p);
+      if (rc) return rc;
+      h->pv[k].geom[r] = static_cast<const double*>(p);
+    }
+    int rc = open(all[size_t(r)].flags, &p);
+    if (rc) return rc;
     pflags[size_t(r)] = static_cast<unsigned long long*>(p);
   }
-  CU(cudaMalloc(&h->d_peers[0], sizeof(double*) * G));
-  CU(cudaMalloc(&h->d_peers[1], sizeof(double*) * G));
   CU(cudaMalloc(&h->d_peer_flags, sizeof(unsigned long long*) * G));
-  CU(cudaMemcpy(h->d_peers[0], peers0.data(), sizeof(double*) * G, cudaMemcpyHostToDevice));
-  CU(cudaMemcpy(h->d_peers[1], peers1.data(), sizeof(double*) * G, cudaMemcpyHostToDevice));
   CU(cudaMemcpy(h->d_peer_flags, pflags.data(), sizeof(unsigned long long*) * G, cudaMemcpyHostToDevice));
-  // everybody must have opened everybody's memory before the first push: one more (tiny) collective
+  // everybody must have opened everybody's memory before the first hand-shake: one more (tiny) collective
   unsigned long long* d_tmp = nullptr;
   CU(cudaMalloc(&d_tmp, sizeof(unsigned long long) * G));
   NC(g_nccl.AllGather(d_tmp + h->rank, d_tmp, sizeof(unsigned long long), ncclChar, h->comm, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   CU(cudaFree(d_tmp));
-  h->parity   = 0;
-  h->ds.peers = nullptr;  // set per step
-  h->p2p      = true;
-  // the hand-shake also carries every rank's displacement bound: neighbour lists work across shards
+  h->p2pctl.peer_flags = h->d_peer_flags;
+  h->p2pctl.flags      = h->d_flags;
+  h->p2pctl.n_ranks    = G;
+  h->p2pctl.rank       = h->rank;
+  h->p2pctl.status     = h->h_status;
+  {
+    const char* e    = getenv("MRSB_P2P_TIMEOUT_MS");
+    h->p2pctl.budget = (e ? atoll(e) : 20000LL) * 2000000LL;  // default 20 s at ~2 GHz SM clock
+  }
+  h->p2p     = true;
+  h->pass_no = 0;
+  // positions, boxes and geometry of the first pass (number 1) live in buffer 1
+  h->ds.gpos = h->gbuf[1];
+  h->ds.gbox = h->d_gbox[1];
+  h->ds.geom = h->d_geom[1];
+  h->n_launches += launch_publish_positions(h->ds, h->stream);
+  h->wrote_since_pass = true;
+  // remote geometry is read from its owner from now on; the hand-shake also carries every rank's displacement bound, so
+  // neighbour lists work across shards
   set_collision_geometry(h, h->grid.nl_count != nullptr);
   drop_collision_graphs(h);
+  CU(cudaStreamSynchronize(h->stream));
   return MRSB_OK;
 }
 
@@ -458,9 +640,12 @@ int mrsb_destroy(mrsb_handle h) {
   if (h->down_stream) cudaStreamDestroy(h->down_stream);
   drop_collision_graphs(h);
   for (void* p : h->ipc_opened) cudaIpcCloseMemHandle(p);
-  if (h->gbuf[1] && h->gbuf[1] != h->ds.gpos) cudaFree(h->gbuf[1]);
-  if (h->gbuf[0] && h->gbuf[0] != h->ds.gpos) cudaFree(h->gbuf[0]);
-  for (void* p : {(void*)h->d_peers[0], (void*)h->d_peers[1], (void*)h->d_flags, (void*)h->d_peer_flags})
+  if (h->p2p || h->gbuf[1]) {  // ds.gpos / ds.geom point at one of the two copies
+    h->ds.gpos = nullptr;
+    for (int k = 0; k < 2; k++)
+      if (h->gbuf[k]) cudaFree(h->gbuf[k]);
+  }
+  for (void* p : {(void*)h->d_geom[0], (void*)h->d_geom[1], (void*)h->d_gbox[0], (void*)h->d_gbox[1], (void*)h->d_flags, (void*)h->d_peer_flags})
     if (p) cudaFree(p);
   if (h->h_status) cudaFreeHost(h->h_status);
   if (h->h_one) cudaFreeHost(h->h_one);
@@ -468,7 +653,8 @@ int mrsb_destroy(mrsb_handle h) {
   void* ptrs[] = {h->ds.st,     h->ds.vprev,  h->ds.rpm,      h->ds.pid,      h->ds.fext,         h->ds.mext,       h->ds.imu,    h->ds.initz,
                   h->ds.cmd,    h->ds.ff,     h->ds.flags,    h->ds.mode,     h->ds.gpos,         h->d_params,      h->d_pset,    h->d_stage,
                   h->d_idx,     h->grid.bucket, h->grid.rank, h->grid.count, h->grid.aabb, h->grid.begin, h->grid.rec, h->grid.pairs,
-                  h->grid.counters, h->cub_tmp, h->grid.nl_count, h->grid.nl_items, h->grid.nl_active, h->grid.ctl};
+                  h->grid.counters, h->grid.scan_state, h->grid.halo_rec, h->grid.halo_bucket, h->grid.halo_rank, h->grid.halo_n,
+                  h->grid.nl_count, h->grid.nl_items, h->grid.nl_active, h->grid.ctl};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -555,6 +741,11 @@ int mrsb_create(const mrsb_create_info* info, mrsb_handle* out) {
   }
   CREATE_CU(cudaMemcpy(h->d_pset, h->pset_host.data(), sizeof(int32_t) * size_t(s.n_global), cudaMemcpyHostToDevice));
   CREATE_RC(flush_params(h));
+  // collision geometry of the whole swarm (the airframe of every UAV is known everywhere at create time)
+  CREATE_RC(dalloc(&h->d_geom[0], 4 * size_t(s.n_global)));
+  s.geom = h->d_geom[0];
+  h->n_launches += launch_set_geom(h->d_geom[0], s.n_global, nullptr, 0, h->d_pset, h->d_params, h->stream);
+  s.opts = STEP_OPT_IMU | STEP_OPT_GPOS;
 
   // initial state (MM:183-198 + setStatePos MM:439-446): R = Rz(-heading), flags from the airframe
   {
@@ -582,12 +773,14 @@ int mrsb_create(const mrsb_create_info* info, mrsb_handle* out) {
   {
     DevGrid&     g  = h->grid;
     const size_t ng = size_t(std::max<int64_t>(s.n_global, 1));
-    // >= 2 buckets per inserted UAV.  A shard inserts its own UAVs plus the halo of remote ones near its
-    // bounding box; the table is sized for a halo of up to 3x the shard (a fuller table only means
-    // longer bucket lists, never wrong results)
-    const size_t expect = std::min(ng, std::max<size_t>(4 * size_t(std::max<int64_t>(s.n, 1)), 512));
+    // >= 1.5 buckets per inserted UAV.  A shard inserts its own UAVs plus the halo of remote ones near its bounding box; the
+    // table is sized for a halo of a quarter of the shard (spatially coherent shards have far less; a fuller table only means
+    // longer bucket lists, never wrong results).  The table is cleared and prefix-summed at every rebuild, so it should not be
+    // larger than it has to be.
+    const size_t own    = size_t(std::max<int64_t>(s.n, 1));
+    const size_t expect = std::max<size_t>(std::min(ng, own + own / 4 + 4096), 512);
     uint32_t     bits   = 10;
-    while ((size_t(1) << bits) < 2 * expect && bits < 30) bits++;
+    while (2 * (size_t(1) << bits) < 3 * expect && bits < 30) bits++;
     g.bits      = bits;
     g.n_buckets = 1u << bits;
     CREATE_RC(dalloc(&g.bucket, ng));
@@ -599,22 +792,30 @@ int mrsb_create(const mrsb_create_info* info, mrsb_handle* out) {
     g.pair_cap = int64_t(std::max<size_t>(4096, 4 * size_t(std::max<int64_t>(s.n, 1))));
     CREATE_RC(dalloc(&g.pairs, 2 * size_t(g.pair_cap)));
     CREATE_RC(dalloc(&g.counters, 4));
-    h->cub_tmp_bytes = collide_tmp_bytes(int64_t(g.n_buckets) + 3, s.n);
-    CREATE_CU(cudaMalloc(&h->cub_tmp, std::max<size_t>(h->cub_tmp_bytes, 16)));
-    // neighbour lists: single-shard handles now, sharded ones once the fused exchange is up (setup_p2p)
+    g.scan_tiles = scan_tiles_for(int64_t(g.n_buckets) + 3);
+    CREATE_RC(dalloc(&g.scan_state, size_t(g.scan_tiles) + size_t(scan_tiles_for(s.n)) + 2));  // table scan + compaction scan
+    // remote UAVs a rebuild fetches from their owners (pull exchange): at most all of them
+    g.halo_cap = std::max<int64_t>(s.n_global - s.n, 1);
+    if (s.n_global > s.n) {
+      CREATE_RC(dalloc(&g.halo_rec, size_t(g.halo_cap)));
+      CREATE_RC(dalloc(&g.halo_bucket, size_t(g.halo_cap)));
+      CREATE_RC(dalloc(&g.halo_rank, size_t(g.halo_cap)));
+    }
+    CREATE_RC(dalloc(&g.halo_n, 1));
+    CREATE_RC(dalloc(&g.ctl, 1));
+    CREATE_CU(cudaHostAlloc(&h->h_one, 2 * sizeof(uint32_t), cudaHostAllocDefault));
+    h->h_one[0] = 1u;
+    h->h_one[1] = 0xFFFFFFFFu;  // "unbounded displacement"
+    // neighbour lists: single-shard handles now, sharded ones once the pull exchange is up (setup_p2p)
     if (s.n > 0 && !getenv("MRSB_NO_NEIGHBOUR_LISTS")) {
       g.nl_ld = s.ld;
       CREATE_RC(dalloc(&g.nl_count, size_t(g.nl_ld)));
       CREATE_RC(dalloc(&g.nl_items, size_t(MRSB_NL_CAP) * size_t(g.nl_ld)));
       CREATE_RC(dalloc(&g.nl_active, size_t(g.nl_ld)));
-      CREATE_RC(dalloc(&g.ctl, 1));
-      CREATE_CU(cudaMemsetAsync(g.ctl, 0, sizeof(NlCtl), h->stream));
-      CREATE_CU(cudaHostAlloc(&h->h_one, 2 * sizeof(uint32_t), cudaHostAllocDefault));
-      h->h_one[0] = 1u;
-      h->h_one[1] = 0xFFFFFFFFu;  // "unbounded displacement"
     }
     set_collision_geometry(h, g.nl_count != nullptr && s.n_global == s.n);
   }
+  make_local_view(h);
   h->shard_begin_of = {s.shard_begin};
   h->shard_count_of = {s.n};
   CREATE_CU(cudaStreamSynchronize(h->stream));
@@ -684,7 +885,10 @@ int mrsb_get_positions_async(mrsb_handle h, double* out_xyz) {
   const int    k     = int(h->n_down & 1);
   const size_t bytes = sizeof(double) * 3 * size_t(h->ds.n);
   if (h->n_down >= 2) CU(cudaStreamWaitEvent(h->stream, h->ev_down[k], 0));  // the snapshot buffer was downloaded two reads ago
-  CU(cudaMemcpyAsync(h->d_snap[k], h->ds.gpos + 3 * h->ds.shard_begin, bytes, cudaMemcpyDeviceToDevice, h->stream));
+  if (!(h->ds.opts & STEP_OPT_GPOS)) return fail(MRSB_ERR_STATE, "packed positions are switched off (mrsb_set_outputs)");
+  // pull exchange: the buffer being written holds the latest positions only once something wrote it since the last pass
+  const double* latest = (h->p2p && !h->wrote_since_pass) ? h->gbuf[h->pass_no & 1] : h->ds.gpos;
+  CU(cudaMemcpyAsync(h->d_snap[k], latest + 3 * h->ds.shard_begin, bytes, cudaMemcpyDeviceToDevice, h->stream));
   CU(cudaEventRecord(h->ev_snap[k], h->stream));
   CU(cudaStreamWaitEvent(h->down_stream, h->ev_snap[k], 0));
   CU(cudaMemcpyAsync(out_xyz, h->d_snap[k], bytes, cudaMemcpyDeviceToHost, h->down_stream));
@@ -826,27 +1030,18 @@ int mrsb_set_feedforward_velocity_hdg_rate(mrsb_handle h, int64_t n, const int32
 }
 int mrsb_set_tracker_cmd(mrsb_handle h, int64_t n, const int32_t* idx, const double* rows) {
   GUARD(h);
-  if (n < 0 || (n > 0 && !rows)) return fail(MRSB_ERR_INVALID, "null payload");
-  // uav_system_ros.cpp:995-1021
-  std::vector<double> vel_hdg(4 * size_t(n)), vel_hdg_rate(4 * size_t(n)), acc_hdg(4 * size_t(n)), acc_hdg_rate(4 * size_t(n));
-  for (int64_t k = 0; k < n; k++) {
-    const double* r  = rows + MRSB_TRACKER_CMD_STRIDE * k;
-    const bool    uh = r[7] != 0.0, uv = r[8] != 0.0, ur = r[9] != 0.0, ua = r[10] != 0.0;
-    const double  v[3]  = {uh ? r[0] : 0.0, uh ? r[1] : 0.0, uv ? r[2] : 0.0};
-    const double  a[3]  = {ua ? r[3] : 0.0, ua ? r[4] : 0.0, ua ? r[5] : 0.0};
-    const double  rate  = ur ? r[6] : 0.0;
-    for (int c = 0; c < 3; c++) {
-      vel_hdg[4 * k + c] = vel_hdg_rate[4 * k + c] = v[c];
-      acc_hdg[4 * k + c] = acc_hdg_rate[4 * k + c] = a[c];
-    }
-    vel_hdg[4 * k + 3] = acc_hdg[4 * k + 3] = 0.0;
-    vel_hdg_rate[4 * k + 3] = acc_hdg_rate[4 * k + 3] = rate;
-  }
-  int rc = mrsb_set_feedforward_velocity_hdg(h, n, idx, vel_hdg.data());
-  if (!rc) rc = mrsb_set_feedforward_velocity_hdg_rate(h, n, idx, vel_hdg_rate.data());
-  if (!rc) rc = mrsb_set_feedforward_acceleration_hdg(h, n, idx, acc_hdg.data());
-  if (!rc) rc = mrsb_set_feedforward_acceleration_hdg_rate(h, n, idx, acc_hdg_rate.data());
-  return rc;
+  const int32_t* d_idx = nullptr;
+  int            rc    = stage_idx(h, n, idx, &d_idx);  // validates n and idx before anything is read
+  if (rc) return rc;
+  if (n == 0) return MRSB_OK;
+  if (!rows) return fail(MRSB_ERR_INVALID, "null payload");
+  const size_t bytes = sizeof(double) * size_t(n) * MRSB_TRACKER_CMD_STRIDE;
+  rc                 = ensure_stage(h, bytes);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(h->d_stage, rows, bytes, cudaMemcpyHostToDevice, h->stream));
+  h->n_launches += launch_tracker_cmd(h->ds, n, d_idx, reinterpret_cast<const double*>(h->d_stage), h->stream);  // ROSW:995-1021 in one kernel
+  CU(cudaGetLastError());
+  return MRSB_OK;
 }
 int mrsb_clear_feedforward(mrsb_handle h, int64_t n, const int32_t* idx) {
   GUARD(h);
@@ -861,16 +1056,8 @@ int mrsb_clear_feedforward(mrsb_handle h, int64_t n, const int32_t* idx) {
 // stepping
 // ------------------------------------------------------------------------------------------
 static int exchange_positions(mrsb_sim* h) {
-  if (h->n_ranks <= 1) return MRSB_OK;
+  if (h->n_ranks <= 1 || h->p2p) return MRSB_OK;  // pull exchange: nothing moves; the pass' first kernel hand-shakes
   if (!h->comm) return fail(MRSB_ERR_STATE, "sharded handle (n_global > n_local) without a communicator: call mrsb_comm_init_nccl, or use mrsb_gather_buffer + mrsb_handle_collisions_gathered");
-  if (h->p2p && h->pushed) {
-    // the step kernel already stored this shard's positions into every peer's buffer: only the
-    // hand-shake "my epoch has landed" / "everybody's has" is left
-    uint32_t* disp = h->lists_on ? &h->grid.ctl->disp_max_bits : nullptr;
-    h->n_launches += launch_p2p_signal(h->d_peer_flags, h->n_ranks, h->rank, h->epoch, disp, h->ds.n > 0 ? 0xFFFFFFFFu : 0u, h->stream);
-    h->n_launches += launch_p2p_wait(h->d_flags, h->n_ranks, h->rank, h->epoch, h->h_status, disp, h->stream);
-    return MRSB_OK;
-  }
   h->positions_touched = true;  // all-gather without the hand-shake: no swarm-wide displacement bound for this pass
   double* buf = h->ds.gpos;
   if (h->equal_shards) {
@@ -886,42 +1073,74 @@ static int exchange_positions(mrsb_sim* h) {
   return MRSB_OK;
 }
 
-// The pass with neighbour lists as ONE graph:  decide -> IF (rebuild) { table, lists } -> check.
+// what the kernels of the collision pass that comes next read: with the pull exchange, the buffers of that pass' parity
+struct PassView {
+  DevState        s;
+  const PeerView* pv;
+  int             k;  // graph slot
+};
+static PassView pass_view(mrsb_sim* h) {
+  PassView v;
+  v.s = h->ds;
+  if (h->p2p) {
+    v.k      = int((h->pass_no + 1) & 1);
+    v.s.gpos = h->gbuf[v.k];
+    v.s.gbox = h->d_gbox[v.k];
+    v.s.geom = h->d_geom[v.k];
+    v.pv     = &h->pv[v.k];
+  } else {
+    v.k  = 0;
+    v.pv = &h->pv_local;
+  }
+  return v;
+}
+
+// decide -> IF (rebuild) { table, lists } -> check, captured into the graph being built on h->stream.
 // The IF node's condition is set on the device by decide_kernel (cudaGraphSetConditional).
-static cudaGraphExec_t build_list_graph(mrsb_sim* h, int* own_fixed, int* own_rebuild) {
+static bool capture_list_pass(mrsb_sim* h, const PassView& v, cudaGraph_t graph, cudaStream_t* side, int* own_fixed, int* own_rebuild) {
+  cudaStreamCaptureStatus status;
+  const cudaGraphNode_t*  deps  = nullptr;
+  size_t                  n_dep = 0;
+  cudaGraphConditionalHandle handle;
+  if (cudaGraphConditionalHandleCreate(&handle, graph, 0, cudaGraphCondAssignDefault) != cudaSuccess) return false;
+  *own_fixed += launch_collide_decide(h->grid, h->p2pctl, 0, handle, 1, h->stream);
+  if (cudaStreamGetCaptureInfo_v2(h->stream, &status, nullptr, &graph, &deps, &n_dep) != cudaSuccess) return false;
+  cudaGraphNodeParams cp = {};
+  cp.type                = cudaGraphNodeTypeConditional;
+  cp.conditional.handle  = handle;
+  cp.conditional.type    = cudaGraphCondTypeIf;
+  cp.conditional.size    = 1;
+  cudaGraphNode_t cond   = nullptr;
+  if (cudaGraphAddNode(&cond, graph, deps, n_dep, &cp) != cudaSuccess) return false;
+  cudaGraph_t body = cp.conditional.phGraph_out[0];
+  if (!*side && cudaStreamCreateWithFlags(side, cudaStreamNonBlocking) != cudaSuccess) return false;
+  if (cudaStreamBeginCaptureToGraph(*side, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal) != cudaSuccess) return false;
+  *own_rebuild = launch_collide_rebuild(v.s, h->grid, *v.pv, *side);
+  cudaGraph_t body_out = nullptr;
+  if (cudaStreamEndCapture(*side, &body_out) != cudaSuccess) return false;
+  if (cudaStreamUpdateCaptureDependencies(h->stream, &cond, 1, cudaStreamSetCaptureDependencies) != cudaSuccess) return false;
+  *own_fixed += launch_collide_check(v.s, h->grid, *v.pv, h->coll_crash, h->coll_rebounce, h->stream);
+  return true;
+}
+
+// The pass with neighbour lists as ONE graph; with_step: preceded by the stepping launch (mrsb_run's tick graph).
+static cudaGraphExec_t build_pass_graph(mrsb_sim* h, const PassView& v, bool with_step, double dt, int k_sub, int* own_fixed, int* own_rebuild) {
   cudaGraph_t     graph = nullptr;
   cudaGraphExec_t exec  = nullptr;
   cudaStream_t    side  = nullptr;
   bool            ok    = false;
+  *own_fixed            = 0;
   if (cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
     cudaGetLastError();
     return nullptr;
   }
   do {
     cudaStreamCaptureStatus status;
-    const cudaGraphNode_t*  deps  = nullptr;
-    size_t                  n_dep = 0;
-    if (cudaStreamGetCaptureInfo_v2(h->stream, &status, nullptr, &graph, &deps, &n_dep) != cudaSuccess || !graph) break;
-    cudaGraphConditionalHandle handle;
-    if (cudaGraphConditionalHandleCreate(&handle, graph, 0, cudaGraphCondAssignDefault) != cudaSuccess) break;
-    *own_fixed = launch_collide_decide(h->grid, 0, handle, 1, h->stream);
-    if (cudaStreamGetCaptureInfo_v2(h->stream, &status, nullptr, &graph, &deps, &n_dep) != cudaSuccess) break;
-    cudaGraphNodeParams cp = {};
-    cp.type                = cudaGraphNodeTypeConditional;
-    cp.conditional.handle  = handle;
-    cp.conditional.type    = cudaGraphCondTypeIf;
-    cp.conditional.size    = 1;
-    cudaGraphNode_t cond   = nullptr;
-    if (cudaGraphAddNode(&cond, graph, deps, n_dep, &cp) != cudaSuccess) break;
-    cudaGraph_t body = cp.conditional.phGraph_out[0];
-    if (cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking) != cudaSuccess) break;
-    if (cudaStreamBeginCaptureToGraph(side, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal) != cudaSuccess) break;
-    *own_rebuild = launch_collide_rebuild(h->ds, h->grid, h->cub_tmp, h->cub_tmp_bytes, side);
-    cudaGraph_t body_out = nullptr;
-    if (cudaStreamEndCapture(side, &body_out) != cudaSuccess) break;
-    if (cudaStreamUpdateCaptureDependencies(h->stream, &cond, 1, cudaStreamSetCaptureDependencies) != cudaSuccess) break;
-    *own_fixed += launch_collide_check(h->ds, h->grid, h->coll_crash, h->coll_rebounce, h->stream);
-    ok = true;
+    if (cudaStreamGetCaptureInfo_v2(h->stream, &status, nullptr, &graph, nullptr, nullptr) != cudaSuccess || !graph) break;
+    if (with_step)
+      *own_fixed += launch_step(h->ds, h->uniform_pset >= 0 ? &h->uniform_params : nullptr, dt, k_sub, h->uniform_mode, h->uniform_nm, h->any_moment, h->stream,
+                                h->step_info);
+    ok = capture_list_pass(h, v, graph, &side, own_fixed, own_rebuild);
   } while (false);
   cudaGraph_t captured = nullptr;
   const bool  ended    = cudaStreamEndCapture(h->stream, &captured) == cudaSuccess && captured;
@@ -932,17 +1151,47 @@ static cudaGraphExec_t build_list_graph(mrsb_sim* h, int* own_fixed, int* own_re
   return exec;
 }
 
+// host bookkeeping before a pass that goes through decide_kernel
+static int before_list_pass(mrsb_sim* h) {
+  // anything but exactly one stepping launch since the last pass: the displacement bound does not cover it
+  if (h->positions_touched || h->steps_since_pass != 1)
+    CU(cudaMemcpyAsync(&h->grid.ctl->force, h->h_one, sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+  h->positions_touched = false;
+  h->steps_since_pass  = 0;
+  h->list_passes++;
+  return MRSB_OK;
+}
+
+// host bookkeeping after any pass: with the pull exchange the write buffer changes sides
+static int after_pass(mrsb_sim* h) {
+  h->n_passes++;
+  if (h->p2p) {
+    h->pass_no++;
+    const int w         = write_buf(h);
+    h->ds.gpos          = h->gbuf[w];
+    h->ds.gbox          = h->d_gbox[w];
+    h->ds.geom          = h->d_geom[w];
+    h->wrote_since_pass = false;
+    int rc              = apply_pending_geom(h, w);  // no peer reads this buffer any more (they have all started the pass that just ran)
+    if (rc) return rc;
+  }
+  CU(cudaGetLastError());
+  return MRSB_OK;
+}
+
 static int collide_local(mrsb_sim* h) {
-  const int k = h->p2p ? h->parity : 0;
+  if (h->p2p && !h->wrote_since_pass) {
+    // nothing wrote positions since the last pass: the buffer this pass reads still holds the ones of two passes ago
+    h->n_launches += launch_publish_positions(h->ds, h->stream);
+    h->wrote_since_pass = true;
+  }
+  const PassView v = pass_view(h);
+  const int      k = v.k;
   if (h->lists_on) {
-    // anything but exactly one stepping launch since the last pass: the displacement bound does not cover it
-    if (h->positions_touched || h->steps_since_pass != 1)
-      CU(cudaMemcpyAsync(&h->grid.ctl->force, h->h_one, sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
-    h->positions_touched = false;
-    h->steps_since_pass  = 0;
-    h->list_passes++;
+    int rc = before_list_pass(h);
+    if (rc) return rc;
     if (!h->coll_graph[k] && !h->list_graph_failed && !getenv("MRSB_NO_GRAPH")) {
-      h->coll_graph[k]     = build_list_graph(h, &h->coll_graph_own[k], &h->rebuild_own);
+      h->coll_graph[k]     = build_pass_graph(h, v, false, 0.0, 0, &h->coll_graph_own[k], &h->rebuild_own);
       h->list_graph_failed = h->coll_graph[k] == nullptr;
     }
     if (h->coll_graph[k]) {
@@ -950,18 +1199,16 @@ static int collide_local(mrsb_sim* h) {
       h->n_launches += h->coll_graph_own[k];  // the rebuilds are added from the device-side count (mrsb_get_counters)
     } else {
       // no graph (MRSB_NO_GRAPH, or conditional nodes unavailable): rebuild every pass
-      h->n_launches += launch_collide_decide(h->grid, 1, cudaGraphConditionalHandle{}, 0, h->stream);
-      h->rebuild_own = launch_collide_rebuild(h->ds, h->grid, h->cub_tmp, h->cub_tmp_bytes, h->stream);
-      h->n_launches += launch_collide_check(h->ds, h->grid, h->coll_crash, h->coll_rebounce, h->stream);
+      h->n_launches += launch_collide_decide(h->grid, h->p2pctl, 1, cudaGraphConditionalHandle{}, 0, h->stream);
+      h->rebuild_own = launch_collide_rebuild(v.s, h->grid, *v.pv, h->stream);
+      h->n_launches += launch_collide_check(v.s, h->grid, *v.pv, h->coll_crash, h->coll_rebounce, h->stream);
     }
-    h->n_passes++;
-    CU(cudaGetLastError());
-    return MRSB_OK;
+    return after_pass(h);
   }
   if (!h->coll_graph[k] && !getenv("MRSB_NO_GRAPH")) {
     cudaGraph_t graph = nullptr;
     if (cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
-      const int own = launch_collide(h->ds, h->grid, h->coll_crash, h->coll_rebounce, h->cub_tmp, h->cub_tmp_bytes, h->stream);
+      const int own = launch_collide(v.s, h->grid, *v.pv, h->p2pctl, h->coll_crash, h->coll_rebounce, h->stream);
       if (cudaStreamEndCapture(h->stream, &graph) == cudaSuccess && graph) {
         if (cudaGraphInstantiate(&h->coll_graph[k], graph, 0) != cudaSuccess) h->coll_graph[k] = nullptr;
         cudaGraphDestroy(graph);
@@ -974,37 +1221,36 @@ static int collide_local(mrsb_sim* h) {
     CU(cudaGraphLaunch(h->coll_graph[k], h->stream));
     h->n_launches += h->coll_graph_own[k];
   } else {
-    h->n_launches += launch_collide(h->ds, h->grid, h->coll_crash, h->coll_rebounce, h->cub_tmp, h->cub_tmp_bytes, h->stream);
+    h->n_launches += launch_collide(v.s, h->grid, *v.pv, h->p2pctl, h->coll_crash, h->coll_rebounce, h->stream);
   }
-  h->n_passes++;
-  CU(cudaGetLastError());
+  h->steps_since_pass = 0;
+  return after_pass(h);
+}
+
+static int before_step(mrsb_sim* h, double dt, int32_t k_substeps) {
+  if (k_substeps < 1) return fail(MRSB_ERR_INVALID, "k_substeps must be >= 1");
+  int rc = flush_params(h);
+  if (rc) return rc;
+  rc = ensure_filt(h, dt);
+  if (rc) return rc;
+  if (h->p2p && *h->h_status) return fail(MRSB_ERR_STATE, "peer hand-shake timed out (a rank stopped calling the collision pass)");
   return MRSB_OK;
 }
 
 int mrsb_make_step(mrsb_handle h, double dt, int32_t k_substeps) {
   GUARD(h);
-  if (k_substeps < 1) return fail(MRSB_ERR_INVALID, "k_substeps must be >= 1");
-  int rc = flush_params(h);
+  int rc = before_step(h, dt, k_substeps);
   if (rc) return rc;
-  if (h->p2p) {
-    if (*h->h_status) return fail(MRSB_ERR_STATE, "peer position exchange timed out (a rank stopped stepping)");
-    h->parity ^= 1;
-    h->ds.gpos  = h->gbuf[h->parity];
-    h->ds.peers = h->d_peers[h->parity];
-    h->epoch++;
-    h->pushed = true;
-  }
   h->n_launches += launch_step(h->ds, h->uniform_pset >= 0 ? &h->uniform_params : nullptr, dt, k_substeps, h->uniform_mode, h->uniform_nm,
                                h->any_moment, h->stream, h->step_info);
+  h->wrote_since_pass = true;
   h->n_steps += k_substeps;
   h->steps_since_pass++;
   CU(cudaGetLastError());
   return MRSB_OK;
 }
 
-int mrsb_handle_collisions(mrsb_handle h) {
-  GUARD(h);
-  if (!(h->coll_crash || h->coll_enabled)) return MRSB_OK;  // SIM:299-301
+static int before_collisions(mrsb_sim* h) {
   int rc = flush_params(h);
   if (rc) return rc;
   if (h->ds.n_global > h->ds.n && h->n_ranks <= 1) return fail(MRSB_ERR_STATE, "sharded handle without communicator");
@@ -1012,6 +1258,14 @@ int mrsb_handle_collisions(mrsb_handle h) {
     // anything but exactly one stepping launch since the last pass: this rank's displacement is unbounded —
     // said through the displacement word, so that every peer rebuilds as well
     CU(cudaMemcpyAsync(&h->grid.ctl->disp_max_bits, h->h_one + 1, sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+  return MRSB_OK;
+}
+
+int mrsb_handle_collisions(mrsb_handle h) {
+  GUARD(h);
+  if (!(h->coll_crash || h->coll_enabled)) return MRSB_OK;  // SIM:299-301
+  int rc = before_collisions(h);
+  if (rc) return rc;
   rc = exchange_positions(h);
   if (rc) return rc;
   return collide_local(h);
@@ -1025,12 +1279,56 @@ int mrsb_handle_collisions_gathered(mrsb_handle h) {
   return collide_local(h);
 }
 
+// One tick = stepping launch + collision pass.  With neighbour lists the two are ONE graph (per buffer parity): a single
+// cudaGraphLaunch per tick instead of a kernel launch plus a graph launch, and no gap between the stepping kernel and the
+// pass' first kernel.  The graph holds its arguments by value, so it is rebuilt when any of them changes.
+static int run_tick_graph(mrsb_sim* h, double dt, int32_t k_substeps, bool* done) {
+  *done = false;
+  if (!h->lists_on || h->tick_failed || h->list_graph_failed || getenv("MRSB_NO_GRAPH") || getenv("MRSB_NO_TICK_GRAPH")) return MRSB_OK;
+  if (h->positions_touched || h->steps_since_pass != 0) return MRSB_OK;  // let the ordinary path sort that out first
+  if (h->tick_dt != dt || h->tick_k != k_substeps || h->tick_mode != h->uniform_mode || h->tick_nm != h->uniform_nm || h->tick_pset != h->uniform_pset ||
+      h->tick_opts != (h->ds.opts | (h->any_moment ? 0x10000u : 0u))) {
+    for (int k = 0; k < 2; k++) {
+      if (h->tick_graph[k]) cudaGraphExecDestroy(h->tick_graph[k]);
+      h->tick_graph[k] = nullptr;
+    }
+    h->tick_dt = dt, h->tick_k = k_substeps, h->tick_mode = h->uniform_mode, h->tick_nm = h->uniform_nm, h->tick_pset = h->uniform_pset,
+    h->tick_opts = h->ds.opts | (h->any_moment ? 0x10000u : 0u);
+    return MRSB_OK;  // this tick goes the ordinary way (first launches set up function attributes: not inside a capture); the next one builds the graph
+  }
+  const PassView v = pass_view(h);
+  if (!h->tick_graph[v.k]) {
+    h->tick_graph[v.k] = build_pass_graph(h, v, true, dt, k_substeps, &h->tick_own[v.k], &h->rebuild_own);
+    if (!h->tick_graph[v.k]) {
+      h->tick_failed = true;
+      return MRSB_OK;
+    }
+  }
+  // bookkeeping of make_step + before_collisions + collide_local for "exactly one stepping launch, then the pass"
+  h->wrote_since_pass = true;
+  h->n_steps += k_substeps;
+  h->list_passes++;
+  CU(cudaGraphLaunch(h->tick_graph[v.k], h->stream));
+  h->n_launches += h->tick_own[v.k];
+  *done = true;
+  return after_pass(h);
+}
+
 int mrsb_run(mrsb_handle h, double dt, int32_t k_substeps, int32_t n_ticks, int32_t with_collisions) {
   GUARD(h);
+  const bool collide = with_collisions && (h->coll_crash || h->coll_enabled);
   for (int t = 0; t < n_ticks; t++) {
+    if (collide) {
+      int rc = before_step(h, dt, k_substeps);
+      if (rc) return rc;
+      bool done = false;
+      rc        = run_tick_graph(h, dt, k_substeps, &done);
+      if (rc) return rc;
+      if (done) continue;
+    }
     int rc = mrsb_make_step(h, dt, k_substeps);
     if (rc) return rc;
-    if (with_collisions) {
+    if (collide) {
       rc = mrsb_handle_collisions(h);
       if (rc) return rc;
     }
@@ -1068,6 +1366,7 @@ int mrsb_get_v_prev(mrsb_handle h, int64_t n, const int32_t* idx, double* v_prev
 
 int mrsb_get_imu_acceleration(mrsb_handle h, int64_t n, const int32_t* idx, double* acc) {
   GUARD(h);
+  if (!(h->ds.opts & STEP_OPT_IMU)) return fail(MRSB_ERR_STATE, "the IMU rows are switched off (mrsb_set_outputs)");
   return get_rows(h, h->ds.imu, F3_ROWS, 0, 3, n, idx, acc);
 }
 
@@ -1088,7 +1387,7 @@ int mrsb_set_state(mrsb_handle h, int64_t n, const int32_t* idx, const double* x
   if (motor_rpm && !rc) rc = put_rows(h, h->ds.rpm, MRSB_NM, 0, MRSB_NM, n, idx, motor_rpm, MRSB_NM, 0);
   if (x && !rc) {
     h->n_launches += launch_publish_positions(h->ds, h->stream);
-    h->pushed            = false;
+    h->wrote_since_pass  = true;
     h->positions_touched = true;
   }
   return rc;
@@ -1108,8 +1407,9 @@ int mrsb_set_state_pos(mrsb_handle h, int64_t n, const int32_t* idx, const doubl
   CU(cudaMemcpyAsync(d_xyz, xyz, sizeof(double) * 3 * size_t(n), cudaMemcpyHostToDevice, h->stream));
   CU(cudaMemcpyAsync(d_hdg, heading, sizeof(double) * size_t(n), cudaMemcpyHostToDevice, h->stream));
   h->n_launches += launch_set_state_pos(h->ds, n, d_idx, d_xyz, d_hdg, h->stream);
+  if (h->p2p) h->n_launches += launch_publish_positions(h->ds, h->stream);  // the whole slice of the buffer being written, and its group boxes
+  h->wrote_since_pass  = true;
   h->positions_touched = true;
-  h->pushed = false;
   CU(cudaGetLastError());
   return MRSB_OK;
 }
@@ -1238,10 +1538,10 @@ int mrsb_set_params(mrsb_handle h, int64_t n, const int32_t* idx, const mrsb_mod
   if (rc) return rc;
   mrsb_controller_params def;
   mrsb_controller_params_default(&def);
-  rc = repoint(h, n, idx, [&](ParamSet& s) {  // US:404-409: new model params, controllers re-created with default gains
+  rc = repoint(h, n, idx, [&](ParamSet& s, int64_t) {  // US:404-409: new model params, controllers re-created with default gains
     s.mp = *params;
     s.cp = def;
-  });
+  }, [](int64_t) { return uint64_t(0); });
   if (rc) return rc;
   const int32_t* d_idx = nullptr;
   rc                   = stage_idx(h, n, idx, &d_idx);
@@ -1252,7 +1552,7 @@ int mrsb_set_params(mrsb_handle h, int64_t n, const int32_t* idx, const mrsb_mod
 }
 
 static int set_ctrl(mrsb_sim* h, int64_t n, const int32_t* idx, int pid_row0, int pid_rows, void (*edit)(ParamSet&, const double*), const double* v) {
-  int rc = repoint(h, n, idx, [&](ParamSet& s) { edit(s, v); });
+  int rc = repoint(h, n, idx, [&](ParamSet& s, int64_t) { edit(s, v); }, [](int64_t) { return uint64_t(0); });
   if (rc) return rc;
   if (pid_rows) {
     const int32_t* d_idx = nullptr;
@@ -1311,6 +1611,7 @@ int mrsb_timeout_input(mrsb_handle h, int64_t n, const int32_t* idx) {
 
 static int observe(mrsb_sim* h, int what, int width, int64_t n, const int32_t* idx, double* out) {
   if (!out) return fail(MRSB_ERR_INVALID, "null output");
+  if ((what == 1 || what == 3) && !(h->ds.opts & STEP_OPT_IMU)) return fail(MRSB_ERR_STATE, "the IMU rows are switched off (mrsb_set_outputs)");
   int rc = flush_params(h);
   if (rc) return rc;
   const int32_t* d_idx = nullptr;
@@ -1340,6 +1641,7 @@ int mrsb_get_rangefinder(mrsb_handle h, int64_t n, const int32_t* idx, double* o
 int mrsb_pack_observations_device(mrsb_handle h, double* out_dev, int32_t stride) {
   GUARD(h);
   if (!out_dev || stride < 17) return fail(MRSB_ERR_INVALID, "need a device buffer with rows of >= 17 doubles");
+  if (!(h->ds.opts & STEP_OPT_IMU)) return fail(MRSB_ERR_STATE, "the IMU rows are switched off (mrsb_set_outputs)");
   int rc = flush_params(h);
   if (rc) return rc;
   h->n_launches += launch_observe(h->ds, 3, h->ds.n, nullptr, out_dev, stride, h->stream);
@@ -1347,31 +1649,39 @@ int mrsb_pack_observations_device(mrsb_handle h, double* out_dev, int32_t stride
   return MRSB_OK;
 }
 
-// set_mass / set_ground_z services: getParams -> edit -> setParams, per UAV (ROSW:1028-1080)
-static int edit_params_each(mrsb_sim* h, int64_t n, const int32_t* idx, const std::function<void(mrsb_model_params&, int64_t)>& edit) {
+// set_mass / set_ground_z services: getParams -> edit -> setParams for every addressed UAV (ROSW:1028-1080), as ONE batched
+// re-pointing: UAVs that share the old parameter set and the new value share the new set; setParams' side effects (controllers
+// back to default gains, PIDs reset, US:404-409) are applied with one launch each.  The take-off patch flag is the UAV's live
+// one (getParams returns it, MM:275), so it does not change.
+static int edit_params_each(mrsb_sim* h, int64_t n, const int32_t* idx, const double* value, void (*edit)(mrsb_model_params&, double)) {
   if (n < 0 || (!idx && n > h->ds.n)) return fail(MRSB_ERR_INVALID, "n=%lld outside 0..%lld", (long long)n, (long long)h->ds.n);
-  std::vector<uint32_t> fl;
-  int                   rc = get_flags(h, n, idx, fl);
+  mrsb_controller_params def;
+  mrsb_controller_params_default(&def);
+  int rc = repoint(h, n, idx, [&](ParamSet& s, int64_t k) {
+    edit(s.mp, value[k]);
+    s.cp = def;
+  }, [&](int64_t k) {
+    uint64_t bits;
+    std::memcpy(&bits, &value[k], sizeof(bits));
+    return bits;
+  });
   if (rc) return rc;
-  for (int64_t k = 0; k < n; k++) {
-    const int32_t     i = idx ? idx[k] : int32_t(k);
-    mrsb_model_params p = h->sets[h->pset_host[size_t(h->ds.shard_begin + i)]].mp;
-    p.takeoff_patch_enabled = (fl[size_t(k)] & FLAG_TAKEOFF) ? 1 : 0;  // getParams returns the live flag (MM:275)
-    edit(p, k);
-    rc = mrsb_set_params(h, 1, &i, &p);
-    if (rc) return rc;
-  }
+  const int32_t* d_idx = nullptr;
+  rc                   = stage_idx(h, n, idx, &d_idx);
+  if (rc) return rc;
+  h->n_launches += launch_reset_pid(h->ds, n, d_idx, 0, PID_ROWS, h->stream);
+  CU(cudaGetLastError());
   return MRSB_OK;
 }
 
 int mrsb_set_mass(mrsb_handle h, int64_t n, const int32_t* idx, const double* mass) {
   GUARD(h);
   if (!mass && n) return fail(MRSB_ERR_INVALID, "null mass");
-  return edit_params_each(h, n, idx, [&](mrsb_model_params& p, int64_t k) {
+  return edit_params_each(h, n, idx, mass, [](mrsb_model_params& p, double m) {
     const double original = p.mass;
-    p.mass                = mass[k];
-    for (int m = 0; m < p.n_motors; m++)
-      p.allocation_matrix[2 * MRSB_MAX_MOTORS + m] = p.mass * (p.allocation_matrix[2 * MRSB_MAX_MOTORS + m] / original);
+    p.mass                = m;
+    for (int k = 0; k < p.n_motors; k++)
+      p.allocation_matrix[2 * MRSB_MAX_MOTORS + k] = p.mass * (p.allocation_matrix[2 * MRSB_MAX_MOTORS + k] / original);
     std::memset(p.J, 0, sizeof(p.J));
     p.J[0] = p.mass * (3.0 * p.arm_length * p.arm_length + p.body_height * p.body_height) / 12.0;
     p.J[4] = p.mass * (3.0 * p.arm_length * p.arm_length + p.body_height * p.body_height) / 12.0;
@@ -1382,19 +1692,48 @@ int mrsb_set_mass(mrsb_handle h, int64_t n, const int32_t* idx, const double* ma
 int mrsb_set_ground_z(mrsb_handle h, int64_t n, const int32_t* idx, const double* ground_z) {
   GUARD(h);
   if (!ground_z && n) return fail(MRSB_ERR_INVALID, "null ground_z");
-  return edit_params_each(h, n, idx, [&](mrsb_model_params& p, int64_t k) { p.ground_z = ground_z[k]; });
+  return edit_params_each(h, n, idx, ground_z, [](mrsb_model_params& p, double z) { p.ground_z = z; });
 }
 
 // ------------------------------------------------------------------------------------------
 // collisions
 // ------------------------------------------------------------------------------------------
+// which optional rows the stepping kernel stores: the caller's wishes plus what the library itself needs
+static int refresh_opts(mrsb_sim* h) {
+  const bool     need_pos = (h->outputs & MRSB_OUT_POSITIONS) || h->coll_enabled || h->coll_crash || h->ds.n_global > h->ds.n;
+  const uint32_t opts     = ((h->outputs & MRSB_OUT_IMU) ? STEP_OPT_IMU : 0u) | (need_pos ? STEP_OPT_GPOS : 0u) | (h->iterate_without_input ? 0u : STEP_OPT_NEED_INPUT);
+  if (opts == h->ds.opts) return MRSB_OK;
+  const bool pos_back = (opts & STEP_OPT_GPOS) && !(h->ds.opts & STEP_OPT_GPOS);
+  h->ds.opts          = opts;
+  drop_collision_graphs(h);
+  if (pos_back) {  // the packed positions were not kept up to date meanwhile
+    h->n_launches += launch_publish_positions(h->ds, h->stream);
+    h->wrote_since_pass  = true;
+    h->positions_touched = true;
+    CU(cudaGetLastError());
+  }
+  return MRSB_OK;
+}
+
 int mrsb_set_collisions(mrsb_handle h, int32_t enabled, int32_t crash, double rebounce) {
   GUARD(h);
   h->coll_enabled  = enabled != 0;
   h->coll_crash    = crash != 0;
   h->coll_rebounce = rebounce;
   drop_collision_graphs(h);
-  return MRSB_OK;
+  return refresh_opts(h);
+}
+
+int mrsb_set_outputs(mrsb_handle h, uint32_t mask) {
+  GUARD(h);
+  h->outputs = mask;
+  return refresh_opts(h);
+}
+
+int mrsb_set_iterate_without_input(mrsb_handle h, int32_t enabled) {
+  GUARD(h);
+  h->iterate_without_input = enabled != 0;
+  return refresh_opts(h);
 }
 
 int mrsb_get_collision_pairs(mrsb_handle h, int32_t* ij, int64_t cap, int64_t* count) {
@@ -1526,11 +1865,10 @@ int mrsb_comm_init_nccl(mrsb_handle h, int32_t n_ranks, int32_t rank, const void
   if (covered != h->ds.n_global) return fail(MRSB_ERR_INVALID, "shards cover %lld UAVs, n_global is %lld", (long long)covered, (long long)h->ds.n_global);
   h->ds.n_ranks = n_ranks;
   h->ds.rank    = rank;
-  if (n_ranks > 1 && n_ranks <= 32 && !getenv("MRSB_NO_P2P")) {
+  if (n_ranks > 1 && n_ranks <= MRSB_MAX_RANKS && !getenv("MRSB_NO_P2P")) {
     if (setup_p2p(h) != MRSB_OK) {  // no peer access (or IPC refused): the NCCL all-gather stays
       cudaGetLastError();
-      h->p2p      = false;
-      h->ds.peers = nullptr;
+      h->p2p = false;
     }
   }
   return MRSB_OK;
@@ -1550,7 +1888,7 @@ int mrsb_gather_buffer(mrsb_handle h, void** device_ptr, size_t* bytes) {
 
 int mrsb_publish_positions(mrsb_handle h) {
   GUARD(h);
-  h->pushed            = false;
+  h->wrote_since_pass  = true;
   h->positions_touched = true;
   h->n_launches += launch_publish_positions(h->ds, h->stream);
   CU(cudaGetLastError());

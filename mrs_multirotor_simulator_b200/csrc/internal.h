@@ -29,6 +29,7 @@ static __host__ __device__ __forceinline__ int64_t tix(int rows, int row, int64_
 #define FLAG_CRASHED 1u        // UavSystem::crashed_ (US:80)
 #define FLAG_TAKEOFF 2u        // live copy of ModelParams::takeoff_patch_enabled (MM:275)
 #define FLAG_VPREV 4u          // v_prev array holds a value different from v (after set_state, MM:424-433)
+#define FLAG_HAD_INPUT 256u    // a command has arrived at least once (UavSystemRos::time_last_input_ > 0, ROSW:265)
 #define FLAG_FF_VEL_HDG_RATE 16u   // std::optional feed-forwards present (US:112-115)
 #define FLAG_FF_VEL_HDG 32u
 #define FLAG_FF_ACC_HDG_RATE 64u
@@ -57,6 +58,8 @@ struct DevParams {
   int32_t j_diagonal;
   double  g, mass, inv_mass, inv_kf_n /* 1/(kf*n_motors) */, min_rpm, rpm_range, inv_rpm_range, neg_inv_tau, air_k /* c*pi*l*l */, ground_z,
       takeoff_rpm /* 0.9*hover_rpm, MM:266-267 */;
+  double  filt;  // exp(-dt / tau) (MM:244) for the dt of the current launches: evaluated ON THE DEVICE by prep_params_kernel (one
+                 // evaluation per parameter set and dt instead of one per UAV and launch; the same bits for every kernel variant)
   double arm_length, prop_radius;  // collision geometry (SIM:342)
   double J[9], Jinv[9];            // row-major
   double alloc[4][MRSB_NM];        // scaled allocation matrix rows: torque xyz, thrust
@@ -85,16 +88,44 @@ struct DevState {
   uint8_t*  mode;   // [ld] INPUT_MODE (US:95)
   const int32_t* pset;  // [n_global] parameter-set index of every UAV of the swarm (local ones at +shard_begin)
   const DevParams* params;
+  double* geom;  // [n_global][4] collision geometry {arm_length, prop_radius, mass, 0} of every UAV of the swarm (SIM:342,350); in
+                       // pull-exchange runs the slots of remote UAVs are a cache of the owners' values (filled with the halo's positions)
   double*  gpos;  // [n_global][3] packed positions: this shard's slice is written by the step kernel
   int64_t  shard_begin;
   int64_t  n_global;
-  // fused position exchange (sharded runs with peer access): the step kernel also stores its positions
-  // into every peer's gather buffer over NVLink.  peers[r] = rank r's buffer (same parity as gpos).
-  double* const* peers;  // device array [n_ranks], nullptr = exchange by NCCL all-gather instead
+  // sharded runs with peer access ("pull" exchange): peers read this shard's slice of gpos straight out of this GPU's memory
+  // over NVLink.  So that a peer can tell which parts of the slice can matter to it, the step kernel also keeps one bounding
+  // box per warp (32 consecutive UAVs): 6 order-preserving uint32 codes of floats rounded outwards, [group][lo xyz, hi xyz].
+  uint32_t* gbox;  // [ld / 32][6], nullptr = not tracked
   int32_t  n_ranks, rank;
+  uint32_t opts;   // STEP_OPT_* bits
   // neighbour lists of the collision pass: the stepping kernel atomicMax-es the float bits of the
   // largest squared displacement |x_end - x_start|^2 of this launch here (nullptr = not tracked)
   uint32_t* disp_max;
+};
+
+#define STEP_OPT_IMU 1u   // store the fabricated accelerometer rows (MM:280-281); off when nobody reads them (mrsb_set_outputs)
+#define STEP_OPT_GPOS 2u  // store the packed positions (collision pass / position download / peers)
+#define STEP_OPT_NEED_INPUT 4u  // iterate_without_input == false (ROSW:265): UAVs that never received a command are not stepped
+
+// Sharded runs: where the current position / collision geometry of a global UAV index lives.  n_ranks == 1: everything is in
+// this handle's own arrays (single shard, or positions gathered into the local buffer by NCCL or by the caller).
+#define MRSB_MAX_RANKS 16
+struct PeerView {
+  int32_t         n_ranks, rank;
+  int64_t         begin[MRSB_MAX_RANKS + 1];  // shard boundaries (global indices)
+  const double*   pos[MRSB_MAX_RANKS];        // rank r's packed positions [n_global][3]; only r's own slice is kept current
+  const uint32_t* box[MRSB_MAX_RANKS];        // rank r's per-group bounding boxes (DevState::gbox)
+  const double*   geom[MRSB_MAX_RANKS];       // rank r's collision geometry [n_global][4]; only r's own slice is kept current
+};
+
+// cross-GPU hand-shake of the pull exchange, done by the first kernel of every collision pass (decide_kernel)
+struct P2PCtl {
+  unsigned long long* const* peer_flags;  // device array [n_ranks]: every rank's flag block (mapped over CUDA IPC)
+  unsigned long long*        flags;       // this rank's block: [0, G) pass numbers written by the peers, [G, 3G) their displacement words
+  int32_t                    n_ranks, rank;  // n_ranks <= 1: no hand-shake
+  int*                       status;      // mapped host word: set to 1 when a peer did not show up in time
+  long long                  budget;      // clock64 ticks to wait for a peer
 };
 
 // neighbour lists (collide.cu): candidates per UAV kept between table rebuilds
@@ -107,7 +138,7 @@ struct NlCtl {
   uint32_t n_crowded;      // UAVs with more than MRSB_NL_CAP candidates at the last rebuild (they walk the table instead)
   uint32_t rebuild;        // decision of the current pass
   double   D_total;        // sum of the per-launch displacement bounds since the last rebuild
-  unsigned long long n_rebuilds, n_passes, reserved_;
+  unsigned long long n_rebuilds, n_passes, epoch /* passes that went through the peer hand-shake */;
   unsigned long long write_all_until;  // host: passes up to this index must write every UAV's force (they were written from outside)
 };
 
@@ -130,6 +161,13 @@ struct DevGrid {
   uint32_t* begin;      // [n_buckets+3] exclusive scan of count; begin[n_buckets] = number of inserted UAVs
   double4*  rec;        // [2*n_global] records {x,y,z, index bits} grouped by bucket (+ the mirror copies of bucket 0)
   unsigned long long* aabb;  // [6] order-preserving encoding of min xyz / max xyz of this shard's positions
+  unsigned long long* scan_state;  // [1 + tiles] ticket counter + per-tile status words of the single-pass prefix sum
+  int32_t   scan_tiles;
+  // pull exchange: remote UAVs that can reach this shard's box, fetched from their owners at a rebuild
+  double4*  halo_rec;   // [halo_cap] {x, y, z, global index}
+  uint32_t* halo_bucket, *halo_rank;  // [halo_cap]
+  uint32_t* halo_n;     // device counter
+  int64_t   halo_cap;
   int32_t*  pairs;      // [pair_cap][2]
   int64_t   pair_cap;
   unsigned long long* counters;  // [0] pairs found by the last pass
@@ -141,19 +179,16 @@ struct DevGrid {
 // [2] NM_T and [3] MODE_T of the instantiation
 int launch_step(const DevState& s, const DevParams* uniform_params, double dt, int k_substeps, int uniform_mode, int uniform_nm, bool any_moment,
                 cudaStream_t stream, int* info);
-int launch_collide(const DevState& s, const DevGrid& g, int crash_mode, double rebounce, void* cub_tmp, size_t cub_tmp_bytes, cudaStream_t stream);
-// the pass with neighbour lists: decide (always) | rebuild (body of the graph's conditional node) | check (always)
-int launch_collide_decide(const DevGrid& g, int always, cudaGraphConditionalHandle handle, int has_handle, cudaStream_t stream);
-int launch_collide_rebuild(const DevState& s, const DevGrid& g, void* cub_tmp, size_t cub_tmp_bytes, cudaStream_t stream);
-int launch_collide_check(const DevState& s, const DevGrid& g, int crash_mode, double rebounce, cudaStream_t stream);
-size_t collide_tmp_bytes(int64_t n_buckets, int64_t n_local);
+// DevParams::filt = exp(dt * neg_inv_tau) for every parameter set of the table
+int launch_prep_params(DevParams* params, int n_sets, double dt, cudaStream_t stream);
+// The full pass of every tick (handles without neighbour lists): [hand-shake,] table, collide_kernel
+int launch_collide(const DevState& s, const DevGrid& g, const PeerView& pv, const P2PCtl& p2p, int crash_mode, double rebounce, cudaStream_t stream);
+// the pass with neighbour lists: decide (always; includes the peer hand-shake) | rebuild (body of the graph's conditional node) | check (always)
+int launch_collide_decide(const DevGrid& g, const P2PCtl& p2p, int always, cudaGraphConditionalHandle handle, int has_handle, cudaStream_t stream);
+int launch_collide_rebuild(const DevState& s, const DevGrid& g, const PeerView& pv, cudaStream_t stream);
+int launch_collide_check(const DevState& s, const DevGrid& g, const PeerView& pv, int crash_mode, double rebounce, cudaStream_t stream);
+int scan_tiles_for(int64_t n_items);
 int launch_publish_positions(const DevState& s, cudaStream_t stream);
-// cross-GPU hand-shake of the fused exchange: tell every peer "my positions of `epoch` have landed", wait for theirs
-// `disp`: this rank's displacement word — sent along with the epoch, and raised to the largest of all ranks' by the wait.
-// A rank that does not track it (nullptr) sends `disp_if_untracked` instead: "unbounded", or 0 if it has no UAVs at all.
-int launch_p2p_signal(unsigned long long* const* peer_flags, int n_ranks, int rank, unsigned long long epoch, const uint32_t* disp,
-                      uint32_t disp_if_untracked, cudaStream_t stream);
-int launch_p2p_wait(const unsigned long long* flags, int n_ranks, int rank, unsigned long long epoch, int* status, uint32_t* disp, cudaStream_t stream);
 
 int launch_scatter_input(const DevState& s, int mode, int64_t n, const int32_t* idx_dev, const double* payload_dev, int stride, cudaStream_t stream);
 // payload[k][0..rows) <-> rows [row0, row0+rows) of a tiled array with `rows_total` components
@@ -170,5 +205,8 @@ int launch_stash_vprev(const DevState& s, int64_t n, const int32_t* idx_dev, cud
 int launch_gather_vprev(const DevState& s, int64_t n, const int32_t* idx_dev, double* out_dev, cudaStream_t stream);
 int launch_reset_pid(const DevState& s, int64_t n, const int32_t* idx_dev, int row0, int rows, cudaStream_t stream);
 int launch_timeout_input(const DevState& s, int64_t n, const int32_t* idx_dev, cudaStream_t stream);
+int launch_tracker_cmd(const DevState& s, int64_t n, const int32_t* idx_dev, const double* rows_dev, cudaStream_t stream);
 int launch_observe(const DevState& s, int what, int64_t n, const int32_t* idx_dev, double* out_dev, int stride, cudaStream_t stream);
 int launch_set_pset(int32_t* pset_dev, int64_t n, const int32_t* idx_dev, int64_t offset, const int32_t* values_dev, cudaStream_t stream);
+// geom[j] = {arm, prop radius, mass, 0} of params[pset[j]] for j = offset + idx[k] (idx == nullptr: j = offset + k), k < n
+int launch_set_geom(double* geom_dev, int64_t n, const int32_t* idx_dev, int64_t offset, const int32_t* pset_dev, const DevParams* params, cudaStream_t stream);

@@ -28,6 +28,7 @@ __global__ void scatter_input_kernel(DevState s, int mode, int64_t n, const int3
     s.cmd[tix(CMD_ROWS, CMD_SIN, i)] = sn;
   }
   s.mode[i] = uint8_t(mode);
+  if (!(s.flags[i] & FLAG_HAD_INPUT)) s.flags[i] |= FLAG_HAD_INPUT;  // time_last_input_ > 0 from now on (ROSW:265)
 }
 
 __global__ void set_mode_kernel(DevState s, int64_t n, const int32_t* __restrict__ idx, int mode) {
@@ -135,12 +136,46 @@ __global__ void set_pset_kernel(int32_t* __restrict__ pset, int64_t n, const int
   pset[offset + at(idx, k)] = values[k];
 }
 
+// UavSystemRos::callbackTrackerCmd (ROSW:987-1022): one tracker command row -> the four sticky feed-forwards.
+// row[11] = velocity xyz | acceleration xyz | heading_rate | use_velocity_horizontal | use_velocity_vertical | use_heading_rate | use_acceleration
+__global__ void tracker_cmd_kernel(DevState s, int64_t n, const int32_t* __restrict__ idx, const double* __restrict__ rows) {
+  const int64_t k = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const int64_t i  = at(idx, k);
+  const double* r  = rows + MRSB_TRACKER_CMD_STRIDE * k;
+  const bool    uh = r[7] != 0.0, uv = r[8] != 0.0, ur = r[9] != 0.0, ua = r[10] != 0.0;
+  const double  v[3] = {uh ? r[0] : 0.0, uh ? r[1] : 0.0, uv ? r[2] : 0.0};
+  const double  a[3] = {ua ? r[3] : 0.0, ua ? r[4] : 0.0, ua ? r[5] : 0.0};
+  for (int c = 0; c < 3; c++) {
+    s.ff[tix(FF_ROWS, FF_VEL_HDG + c, i)]      = v[c];
+    s.ff[tix(FF_ROWS, FF_VEL_HDG_RATE + c, i)] = v[c];
+    s.ff[tix(FF_ROWS, FF_ACC_HDG + c, i)]      = a[c];
+    s.ff[tix(FF_ROWS, FF_ACC_HDG_RATE + c, i)] = a[c];
+  }
+  s.ff[tix(FF_ROWS, FF_ACC_HDG_RATE + 3, i)] = ur ? r[6] : 0.0;
+  s.flags[i] |= FLAG_FF_VEL_HDG | FLAG_FF_VEL_HDG_RATE | FLAG_FF_ACC_HDG | FLAG_FF_ACC_HDG_RATE;
+}
+
+// collision geometry of the addressed UAVs from their parameter set
+__global__ void set_geom_kernel(double* __restrict__ geom, int64_t n, const int32_t* __restrict__ idx, int64_t offset, const int32_t* __restrict__ pset,
+                                const DevParams* __restrict__ params) {
+  const int64_t k = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const int64_t    j = offset + at(idx, k);
+  const DevParams& P = params[pset[j]];
+  geom[4 * j + 0]    = P.arm_length;
+  geom[4 * j + 1]    = P.prop_radius;
+  geom[4 * j + 2]    = P.mass;
+  geom[4 * j + 3]    = 0.0;
+}
+
 // UavSystemRos::timeoutInput (ROSW:474-647): the active command becomes its "hover" version
 __global__ void timeout_input_kernel(DevState s, int64_t n, const int32_t* __restrict__ idx) {
   const int64_t k = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (k >= n) return;
   const int64_t i    = at(idx, k);
   const int     mode = s.mode[i];
+  s.flags[i] &= ~FLAG_HAD_INPUT;  // time_last_input_ = 0 (ROSW:256-259): with iterate_without_input off the UAV stops until the next command
   auto          C    = [&](int row) -> double& { return s.cmd[tix(CMD_ROWS, row, i)]; };
   auto          S    = [&](int row) { return s.st[tix(ST_ROWS, row, i)]; };
   const double  hdg  = atan2(S(7), S(6));  // AttitudeConverter(R).getHeading(): atan2(R10, R00)
@@ -311,6 +346,16 @@ int launch_gather_vprev(const DevState& s, int64_t n, const int32_t* idx, double
 int launch_reset_pid(const DevState& s, int64_t n, const int32_t* idx, int row0, int rows, cudaStream_t st) {
   if (n <= 0) return 0;
   reset_pid_kernel<<<nblk(n), 256, 0, st>>>(s, n, idx, row0, rows);
+  return 1;
+}
+int launch_tracker_cmd(const DevState& s, int64_t n, const int32_t* idx, const double* rows, cudaStream_t st) {
+  if (n <= 0) return 0;
+  tracker_cmd_kernel<<<nblk(n), 256, 0, st>>>(s, n, idx, rows);
+  return 1;
+}
+int launch_set_geom(double* geom, int64_t n, const int32_t* idx, int64_t offset, const int32_t* pset, const DevParams* params, cudaStream_t st) {
+  if (n <= 0) return 0;
+  set_geom_kernel<<<nblk(n), 256, 0, st>>>(geom, n, idx, offset, pset, params);
   return 1;
 }
 int launch_set_pset(int32_t* pset, int64_t n, const int32_t* idx, int64_t offset, const int32_t* values, cudaStream_t st) {

@@ -1,6 +1,6 @@
 // step_kernel.cu — dispatch of the stepping kernels (step_kernel.cuh, instantiated per motor count in
-// step_kernel_nm*.cu) plus the small kernels around them: position publishing and the cross-GPU
-// hand-shake of the fused exchange.
+// step_kernel_nm*.cu) plus the small kernels around them: position publishing and the per-launch
+// parameter preparation.
 #include <cstdlib>
 
 #include "internal.h"
@@ -32,69 +32,58 @@ int launch_step(const DevState& s, const DevParams* uniform_params, double dt, i
 }
 
 namespace {
-__global__ void publish_positions_kernel(DevState s) {
-  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= s.n) return;
-  double* gp = s.gpos + 3 * (s.shard_begin + i);
-  gp[0]      = s.st[tix(ST_ROWS, 0, i)];
-  gp[1]      = s.st[tix(ST_ROWS, 1, i)];
-  gp[2]      = s.st[tix(ST_ROWS, 2, i)];
+__device__ __forceinline__ uint32_t fenc(float f) {
+  const uint32_t b = __float_as_uint(f);
+  return (b >> 31) ? ~b : (b | 0x80000000u);
 }
 
-// Flag block of a rank: [0, G) epochs written by the peers; [G, 3G) the peers' displacement words
-// (float bits of the largest squared displacement of their stepping launch), double-buffered by epoch
-// parity — a peer is at most one tick ahead, so the slot of epoch e is not overwritten before e + 2.
-__global__ void p2p_signal_kernel(unsigned long long* const* peer_flags, int n_ranks, int rank, unsigned long long epoch, const uint32_t* disp,
-                                  uint32_t disp_if_untracked) {
-  const int r = threadIdx.x;
-  if (r < n_ranks && r != rank)
-    *reinterpret_cast<volatile unsigned long long*>(peer_flags[r] + n_ranks + 2 * rank + int(epoch & 1ull)) =
-        (unsigned long long)(disp ? *disp : disp_if_untracked);
-  __threadfence_system();
-  if (r < n_ranks && r != rank) *reinterpret_cast<volatile unsigned long long*>(peer_flags[r] + rank) = epoch;
-}
-// one lane per peer spins (bounded) on this rank's own flag slots, which the peers write over NVLink
-__global__ void p2p_wait_kernel(const unsigned long long* flags, int n_ranks, int rank, unsigned long long epoch, int* status, long long budget,
-                                uint32_t* disp) {
-  const int r = threadIdx.x;
-  if (r < n_ranks && r != rank) {
-    const long long t0 = clock64();
-    bool            ok = true;
-    while (*reinterpret_cast<const volatile unsigned long long*>(flags + r) < epoch) {
-      if (clock64() - t0 > budget) {  // a peer is gone; report instead of hanging the GPU
-        *status = 1;
-        ok      = false;
-        break;
-      }
-      __nanosleep(64);
-    }
-    if (disp) {
-      // the swarm-wide displacement bound: the largest of every rank's (a lost peer counts as "unbounded")
-      __threadfence_system();
-      const uint32_t theirs = ok ? uint32_t(*reinterpret_cast<const volatile unsigned long long*>(flags + n_ranks + 2 * r + int(epoch & 1ull))) : 0xFFFFFFFFu;
-      atomicMax(disp, theirs);
+// positions of the state -> packed buffer (after set_state / a parity flip), plus the per-warp bounding boxes the peers filter by
+__global__ void __launch_bounds__(256) publish_positions_kernel(DevState s) {
+  const int64_t i      = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;  // blockDim is a multiple of 32: warps coincide with the 32-UAV groups
+  const bool    inside = i < s.n;
+  double        x = 0.0, y = 0.0, z = 0.0;
+  if (inside) {
+    x          = s.st[tix(ST_ROWS, 0, i)];
+    y          = s.st[tix(ST_ROWS, 1, i)];
+    z          = s.st[tix(ST_ROWS, 2, i)];
+    double* gp = s.gpos + 3 * (s.shard_begin + i);
+    gp[0]      = x;
+    gp[1]      = y;
+    gp[2]      = z;
+  }
+  if (s.gbox) {
+    const uint32_t full = 0xffffffffu;
+    uint32_t lo0 = inside ? fenc(__double2float_rd(x)) : 0xFFFFFFFFu, lo1 = inside ? fenc(__double2float_rd(y)) : 0xFFFFFFFFu,
+             lo2 = inside ? fenc(__double2float_rd(z)) : 0xFFFFFFFFu;
+    uint32_t hi0 = inside ? fenc(__double2float_ru(x)) : 0u, hi1 = inside ? fenc(__double2float_ru(y)) : 0u, hi2 = inside ? fenc(__double2float_ru(z)) : 0u;
+    lo0 = __reduce_min_sync(full, lo0);
+    lo1 = __reduce_min_sync(full, lo1);
+    lo2 = __reduce_min_sync(full, lo2);
+    hi0 = __reduce_max_sync(full, hi0);
+    hi1 = __reduce_max_sync(full, hi1);
+    hi2 = __reduce_max_sync(full, hi2);
+    if ((threadIdx.x & 31) == 0 && i < s.ld) {
+      uint32_t* row = s.gbox + 6 * (i >> 5);
+      row[0] = lo0, row[1] = lo1, row[2] = lo2, row[3] = hi0, row[4] = hi1, row[5] = hi2;
     }
   }
+}
+
+// exp(-dt / tau) (MM:244) once per parameter set, on the device: every stepping-kernel variant reads the same bits
+__global__ void prep_params_kernel(DevParams* params, int n_sets, double dt) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n_sets) params[k].filt = exp(dt * params[k].neg_inv_tau);
 }
 }  // namespace
 
-int launch_p2p_signal(unsigned long long* const* peer_flags, int n_ranks, int rank, unsigned long long epoch, const uint32_t* disp,
-                      uint32_t disp_if_untracked, cudaStream_t stream) {
-  p2p_signal_kernel<<<1, 32, 0, stream>>>(peer_flags, n_ranks, rank, epoch, disp, disp_if_untracked);
-  return 1;
-}
-int launch_p2p_wait(const unsigned long long* flags, int n_ranks, int rank, unsigned long long epoch, int* status, uint32_t* disp, cudaStream_t stream) {
-  static long long budget = 0;
-  if (!budget) {
-    const char* e = getenv("MRSB_P2P_TIMEOUT_MS");
-    budget        = (e ? atoll(e) : 20000LL) * 2000000LL;  // default 20 s at ~2 GHz SM clock
-  }
-  p2p_wait_kernel<<<1, 32, 0, stream>>>(flags, n_ranks, rank, epoch, status, budget, disp);
+int launch_prep_params(DevParams* params, int n_sets, double dt, cudaStream_t stream) {
+  if (n_sets <= 0) return 0;
+  prep_params_kernel<<<(n_sets + 127) / 128, 128, 0, stream>>>(params, n_sets, dt);
   return 1;
 }
 
 int launch_publish_positions(const DevState& s, cudaStream_t stream) {
   if (s.n <= 0) return 0;
-  publish_positions_kernel<<<unsigned((s.n + 255) / 256), 256, 0, stream>>>(s);
+  publish_positions_kernel<<<unsigned((s.ld + 255) / 256), 256, 0, stream>>>(s);
   return 1;
 }

@@ -161,6 +161,9 @@ struct Slope {
 // MultirotorModel::operator() (MM:301-366) without the x_dot = v rows (handled by the caller).
 // NaN slopes are scrubbed to zero element by element (MM:361-365): always when EXACT, otherwise only
 // after an integer screen of the exponent fields found something Inf/NaN.
+// (Tried and dropped, profiles/r2/history.md: skipping the re-orthonormalisation in the first RK stage, whose input left the
+// previous step's closing reortho — no measurable time at K = 1, and in open-loop tumbling flight the missing projection lets
+// the trajectories drift from the reference's by 1e-3 m after 10 s instead of 1e-11 m.)
 template <bool EXACT>
 DEV Slope derivative(Vec3 v, const Rot& Rraw, Vec3 w, const Frozen& f, const DevParams* __restrict__ P, bool jdiag, Vec3 Jd, Vec3 Jdi, unsigned& screen) {
   Slope        k;
@@ -324,15 +327,31 @@ DEV void tma_load(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t
                : "memory");
 }
 
-// 1-D bulk copy shared -> global (local HBM or a peer's, over NVLink) through the TMA unit
-DEV void tma_store(void* gmem_dst, const void* smem_src, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+// order-preserving code of a float (for integer min / max); fdec() in collide.cu is its inverse
+DEV uint32_t fenc(float f) {
+  const uint32_t b = __float_as_uint(f);
+  return (b >> 31) ? ~b : (b | 0x80000000u);
 }
-DEV void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N>
-DEV void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
-DEV void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-DEV void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// Bounding box of the 32 UAVs of this warp, rounded outwards to float: six warp reductions (REDUX), one 24-byte row per warp.
+// Lanes past the end of the shard contribute nothing; a NaN coordinate yields a NaN bound, which every reader treats as
+// "cannot be excluded".
+DEV void store_group_box(uint32_t* row, bool inside, Vec3 x) {
+  const uint32_t full = 0xffffffffu;
+  uint32_t lo0 = inside ? fenc(__double2float_rd(x.x)) : 0xFFFFFFFFu, lo1 = inside ? fenc(__double2float_rd(x.y)) : 0xFFFFFFFFu,
+           lo2 = inside ? fenc(__double2float_rd(x.z)) : 0xFFFFFFFFu;
+  uint32_t hi0 = inside ? fenc(__double2float_ru(x.x)) : 0u, hi1 = inside ? fenc(__double2float_ru(x.y)) : 0u, hi2 = inside ? fenc(__double2float_ru(x.z)) : 0u;
+  lo0 = __reduce_min_sync(full, lo0);
+  lo1 = __reduce_min_sync(full, lo1);
+  lo2 = __reduce_min_sync(full, lo2);
+  hi0 = __reduce_max_sync(full, hi0);
+  hi1 = __reduce_max_sync(full, hi1);
+  hi2 = __reduce_max_sync(full, hi2);
+  if ((threadIdx.x & 31) == 0) {
+    reinterpret_cast<uint2*>(row)[0] = make_uint2(lo0, lo1);
+    reinterpret_cast<uint2*>(row)[1] = make_uint2(lo2, hi0);
+    reinterpret_cast<uint2*>(row)[2] = make_uint2(hi1, hi2);
+  }
+}
 
 // where one thread reads its UAV's inputs: tile base + lane, rows 128 doubles apart — either the
 // tile in HBM (direct kernel) or its copy in shared memory (staged kernel)
@@ -346,15 +365,17 @@ struct TileIn {
 // per thread after the last read through `in` (the staged kernel re-arms its TMA there).
 template <int NM_T, int MODE_T, bool ONE, class Hook>
 DEV void step_uav(const DevState& s, const TileIn& in, const int64_t tile, const uint32_t flags0, const DevParams* batch_params, const int32_t pset,
-                  const double dt, const int k_sub_arg, const int any_moment, double* xyz_stage, uint32_t& disp_bits, Hook after_loads) {
+                  const double dt, const double inv_dt, const int k_sub_arg, const int any_moment, uint32_t& disp_bits, Hook after_loads) {
   // batch_params: the whole batch's single parameter set in the constant bank (staged kernel), or
   // nullptr -> this UAV's entry of the table in HBM (read-only path)
   const DevParams* __restrict__ P = batch_params ? batch_params : s.params + pset;
   const int k_sub = ONE ? 1 : k_sub_arg;
   static_assert(MRSB_STEP_THREADS == MRSB_TILE, "one CTA per 128-UAV tile");
-  const int64_t i_raw = tile * MRSB_TILE + threadIdx.x;
-  const bool    valid = i_raw < s.n;  // lanes past the end of the last tile compute on padding and store nothing
-  const int64_t i     = valid ? i_raw : s.n - 1;
+  const int64_t i_raw  = tile * MRSB_TILE + threadIdx.x;
+  const bool    inside = i_raw < s.n;  // lanes past the end of the last tile compute on padding and store nothing
+  // ROSW:265: with iterate_without_input off, a UAV that never received a command is not stepped at all: nothing of it is stored
+  const bool    valid  = inside && !((s.opts & STEP_OPT_NEED_INPUT) && !(flags0 & FLAG_HAD_INPUT));
+  const int64_t i      = inside ? i_raw : s.n - 1;
   // tile base pointers: every access below is [pointer + compile-time offset]
   const double* const t_st   = in.st;
   const double* const t_rpm  = in.rpm;
@@ -464,8 +485,7 @@ DEV void step_uav(const DevState& s, const TileIn& in, const int64_t tile, const
   after_loads();  // nothing below reads through `in`
 
   // ---- per-launch constants ---------------------------------------------------------------
-  const double inv_dt   = 1.0 / dt;
-  const double filt     = exp(dt * P->neg_inv_tau);  // MM:244
+  const double filt     = P->filt;  // exp(-dt / tau), MM:244 (prep_params_kernel)
   const double inv_mass = P->inv_mass;
   const double g        = P->g;
   const bool   jdiag    = P->j_diagonal != 0;
@@ -747,40 +767,27 @@ DEV void step_uav(const DevState& s, const TileIn& in, const int64_t tile, const
   ST(o_st, 15, w.x);
   ST(o_st, 16, w.y);
   ST(o_st, 17, w.z);
-  ST(o_imu, 0, imu.x);
-  ST(o_imu, 1, imu.y);
-  ST(o_imu, 2, imu.z);
+  if (s.opts & STEP_OPT_IMU) {
+    ST(o_imu, 0, imu.x);
+    ST(o_imu, 1, imu.y);
+    ST(o_imu, 2, imu.z);
+  }
   const uint32_t new_flags = flags & ~FLAG_VPREV;
+  if (!valid) x = x_start;  // frozen: its position is published unchanged
   if (valid) {
     // squared displacement of this launch as float bits, rounded up (NaN keeps the largest pattern)
     const double ddx = x.x - x_start.x, ddy = x.y - x_start.y, ddz = x.z - x_start.z;
     disp_bits = max(disp_bits, __float_as_uint(fabsf(__double2float_ru(fma(ddx, ddx, fma(ddy, ddy, ddz * ddz))))));
     if (new_flags != flags0) s.flags[i] = new_flags;
-    // packed position for the collision pass / the cross-shard all-gather
-    const int64_t go = 3 * (s.shard_begin + i);
-    if (xyz_stage) {
-      // staged kernel, full tile: the packed positions of the tile leave through shared memory as
-      // bulk copies to the local gather buffer and to every peer (issued by the caller)
-      xyz_stage[3 * threadIdx.x + 0] = x.x;
-      xyz_stage[3 * threadIdx.x + 1] = x.y;
-      xyz_stage[3 * threadIdx.x + 2] = x.z;
-    } else {
-      double* gp = s.gpos + go;
-      gp[0]      = x.x;
-      gp[1]      = x.y;
-      gp[2]      = x.z;
-      if (s.peers) {
-        // fused all-gather: the same 24 bytes go straight into every peer's buffer (posted NVLink stores)
-        for (int r = 0; r < s.n_ranks; r++) {
-          if (r == s.rank) continue;
-          double* pp = s.peers[r] + go;
-          pp[0]      = x.x;
-          pp[1]      = x.y;
-          pp[2]      = x.z;
-        }
-      }
-    }
   }
+  if (inside && (s.opts & STEP_OPT_GPOS)) {
+    // packed position for the collision pass / position download / the peers that pull it over NVLink
+    double* gp = s.gpos + 3 * (s.shard_begin + i);
+    gp[0]      = x.x;
+    gp[1]      = x.y;
+    gp[2]      = x.z;
+  }
+  if (s.gbox) store_group_box(s.gbox + 6 * (tile * (MRSB_TILE / 32) + (threadIdx.x >> 5)), inside, x);
 #undef LD
 #undef ST
 }
@@ -795,7 +802,8 @@ DEV void report_displacement(const DevState& s, uint32_t disp_bits) {
 
 // ---- direct kernel: one CTA per tile, inputs read straight from HBM ----------------------------
 template <int NM_T, int MODE_T, bool ONE>
-__global__ void __launch_bounds__(MRSB_STEP_THREADS, MRSB_STEP_MINB(ONE, MODE_T)) uav_step_kernel(DevState s, double dt, int k_sub, int any_moment) {
+__global__ void __launch_bounds__(MRSB_STEP_THREADS, MRSB_STEP_MINB(ONE, MODE_T))
+    uav_step_kernel(DevState s, double dt, double inv_dt, int k_sub, int any_moment) {
   const int64_t tile = blockIdx.x;
   TileIn        in;
   in.st   = s.st + (tile * ST_ROWS) * MRSB_TILE + threadIdx.x;
@@ -805,7 +813,7 @@ __global__ void __launch_bounds__(MRSB_STEP_THREADS, MRSB_STEP_MINB(ONE, MODE_T)
   in.fext = s.fext + (tile * F3_ROWS) * MRSB_TILE + threadIdx.x;
   const int64_t i = min(tile * MRSB_TILE + threadIdx.x, s.n - 1);
   uint32_t disp_bits = 0u;
-  step_uav<NM_T, MODE_T, ONE>(s, in, tile, s.flags[i], nullptr, s.pset[s.shard_begin + i], dt, k_sub, any_moment, nullptr, disp_bits, [] {});
+  step_uav<NM_T, MODE_T, ONE>(s, in, tile, s.flags[i], nullptr, s.pset[s.shard_begin + i], dt, inv_dt, k_sub, any_moment, disp_bits, [] {});
   report_displacement(s, disp_bits);
 }
 
@@ -837,14 +845,12 @@ DEV void stage_tile(const DevState& s, double* sm, uint64_t* bar, int64_t tile) 
   tma_load(sm + SM_FEXT * MRSB_TILE, s.fext + (tile * F3_ROWS) * MRSB_TILE, kRow * F3_ROWS, bar);
 }
 
-// BULK: the shard has peers — the tile's packed positions leave through shared memory as TMA bulk
-// stores to the local gather buffer and to every peer's (fused all-gather over NVLink).
-template <int NM_T, int MODE_T, bool ONE, bool BULK>
+template <int NM_T, int MODE_T, bool ONE>
 __global__ void __launch_bounds__(MRSB_STEP_THREADS, MRSB_STEP_MINB(ONE, MODE_T))
-    uav_step_staged_kernel(DevState s, const __grid_constant__ DevParams params, double dt, int k_sub, int any_moment, int64_t n_tiles) {
+    uav_step_staged_kernel(DevState s, const __grid_constant__ DevParams params, double dt, double inv_dt, int k_sub, int any_moment, int64_t n_tiles) {
   // `params`: the one parameter set of the whole batch, passed BY VALUE: it lives in the constant
   // bank, so airframe constants and gains are instruction operands instead of ~80 loads per UAV
-  extern __shared__ __align__(128) double sm[];  // SM_ROWS x 128 doubles (tile image) + 2 x 3 x 128 (outgoing positions)
+  extern __shared__ __align__(128) double sm[];  // SM_ROWS x 128 doubles (tile image)
   __shared__ uint64_t bar;
   if (threadIdx.x == 0) mbar_init(&bar, 1);
   __syncthreads();
@@ -857,12 +863,6 @@ __global__ void __launch_bounds__(MRSB_STEP_THREADS, MRSB_STEP_MINB(ONE, MODE_T)
   in.cmd  = sm + SM_CMD * MRSB_TILE + threadIdx.x;
   in.fext = sm + SM_FEXT * MRSB_TILE + threadIdx.x;
   uint32_t phase = 0;
-  // packed positions of a tile (128 x 24 B) leave through two alternating staging buffers
-  double* const xyz_out  = sm + SM_ROWS * MRSB_TILE;
-  // only when there are peers to feed (a single shard stores its 24 bytes per UAV directly: measured
-  // faster than the extra barrier); needs 16-byte alignment of every tile's slice of the gather buffer
-  const bool    bulk_ok  = BULK && s.peers != nullptr && (s.shard_begin & 1) == 0;
-  uint32_t      out_slot = 0;
   // the per-UAV word that is not part of the tile image is prefetched one tile ahead
   int64_t  i0        = min(tile * MRSB_TILE + threadIdx.x, s.n - 1);
   uint32_t flags_cur = tile < n_tiles ? s.flags[i0] : 0u;
@@ -871,43 +871,23 @@ __global__ void __launch_bounds__(MRSB_STEP_THREADS, MRSB_STEP_MINB(ONE, MODE_T)
     const int64_t next = tile + gridDim.x;
     uint32_t      flags_next = 0u;
     if (next < n_tiles) flags_next = s.flags[min(next * MRSB_TILE + threadIdx.x, s.n - 1)];
-    const bool full  = BULK && bulk_ok && (tile + 1) * MRSB_TILE <= s.n;  // partial last tile: plain stores
-    double*    stage = (BULK && full) ? xyz_out + out_slot * (3 * MRSB_TILE) : nullptr;
     mbar_wait(&bar, phase);
     phase ^= 1u;
-    step_uav<NM_T, MODE_T, ONE>(s, in, tile, flags_cur, &params, 0, dt, k_sub, any_moment, stage, disp_bits, [&] {
-      if (BULK && threadIdx.x == 0) tma_store_wait_read<1>();  // the staging buffer about to be refilled has been read out
+    step_uav<NM_T, MODE_T, ONE>(s, in, tile, flags_cur, &params, 0, dt, inv_dt, k_sub, any_moment, disp_bits, [&] {
       __syncthreads();  // every lane has its inputs in registers: the image may be overwritten
       if (threadIdx.x == 0 && next < n_tiles) stage_tile<NM_T, MODE_T>(s, sm, &bar, next);
     });
-    if (BULK && full) {
-      fence_async_smem();
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        constexpr uint32_t kBytes = 3 * MRSB_TILE * sizeof(double);
-        const int64_t      go     = 3 * (s.shard_begin + tile * MRSB_TILE);
-        tma_store(s.gpos + go, stage, kBytes);
-        if (s.peers) {
-          // fused all-gather: the tile's positions go to every peer's buffer over NVLink as bulk copies
-          for (int r = 0; r < s.n_ranks; r++)
-            if (r != s.rank) tma_store(s.peers[r] + go, stage, kBytes);
-        }
-        tma_store_commit();
-      }
-      out_slot ^= 1u;
-    }
     flags_cur = flags_next;
   }
-  if (BULK && threadIdx.x == 0) tma_store_wait_all();
   report_displacement(s, disp_bits);
 }
 
 // CTAs of the staged kernel that fit on the device (persistent grid), cached per instantiation
-template <int NM_T, int MODE_T, bool ONE, bool BULK>
+template <int NM_T, int MODE_T, bool ONE>
 int staged_grid(size_t smem) {
   static int cached = -1;
   if (cached < 0) {
-    auto* k = uav_step_staged_kernel<NM_T, MODE_T, ONE, BULK>;
+    auto* k = uav_step_staged_kernel<NM_T, MODE_T, ONE>;
     if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess) {
       cudaGetLastError();
       cached = 0;
@@ -926,36 +906,30 @@ template <int NM_T, int MODE_T>
 void launch_one(const DevState& s, const DevParams* uniform_params, double dt, int k, int any_moment, cudaStream_t st, int* info) {
   const int     threads = MRSB_STEP_THREADS;
   const int64_t n_tiles = (s.n + threads - 1) / threads;
+  const double  inv_dt  = 1.0 / dt;
   info[2] = NM_T;
   info[3] = MODE_T;
-  if constexpr (NM_T > 0 && MODE_T >= 0) if (uniform_params) {
+  if constexpr (NM_T > 0 && MODE_T >= 0) if (uniform_params && !getenv("MRSB_NO_STAGING")) {
     // enough tiles to fill the machine more than once: persistent CTAs + TMA staging hide the HBM
     // latency behind the integration of the previous tile
-    const bool   bulk = s.peers != nullptr;
-    const size_t smem = (size_t(SM_ROWS) + (bulk ? 6 : 0)) * MRSB_TILE * sizeof(double);  // tile image (+ two xyz staging buffers)
-    auto launch = [&](auto one, auto blk) -> bool {
-      constexpr bool kOne = decltype(one)::value, kBulk = decltype(blk)::value;
-      const int      grid = staged_grid<NM_T, MODE_T, kOne, kBulk>(smem);
+    const size_t smem = size_t(SM_ROWS) * MRSB_TILE * sizeof(double);
+    auto launch = [&](auto one) -> bool {
+      constexpr bool kOne = decltype(one)::value;
+      const int      grid = staged_grid<NM_T, MODE_T, kOne>(smem);
       if (grid <= 0 || n_tiles <= grid) return false;
-      uav_step_staged_kernel<NM_T, MODE_T, kOne, kBulk><<<grid, threads, smem, st>>>(s, *uniform_params, dt, k, any_moment, n_tiles);
-      info[0] = kBulk ? 3 : 2;
+      uav_step_staged_kernel<NM_T, MODE_T, kOne><<<grid, threads, smem, st>>>(s, *uniform_params, dt, inv_dt, k, any_moment, n_tiles);
+      info[0] = 2;
       info[1] = grid;
       return true;
     };
-    if (!getenv("MRSB_NO_STAGING")) {
-      // enough tiles to fill the machine more than once: persistent CTAs + TMA staging hide the HBM
-      // latency behind the integration of the previous tile
-      const bool done = (k == 1) ? (bulk ? launch(std::true_type{}, std::true_type{}) : launch(std::true_type{}, std::false_type{}))
-                                 : (bulk ? launch(std::false_type{}, std::true_type{}) : launch(std::false_type{}, std::false_type{}));
-      if (done) return;
-    }
+    if ((k == 1) ? launch(std::true_type{}) : launch(std::false_type{})) return;
   }
   info[0] = 1;
   info[1] = int(n_tiles);
   if (k == 1) {
-    uav_step_kernel<NM_T, MODE_T, true><<<unsigned(n_tiles), threads, 0, st>>>(s, dt, k, any_moment);
+    uav_step_kernel<NM_T, MODE_T, true><<<unsigned(n_tiles), threads, 0, st>>>(s, dt, inv_dt, k, any_moment);
   } else {
-    uav_step_kernel<NM_T, MODE_T, false><<<unsigned(n_tiles), threads, 0, st>>>(s, dt, k, any_moment);
+    uav_step_kernel<NM_T, MODE_T, false><<<unsigned(n_tiles), threads, 0, st>>>(s, dt, inv_dt, k, any_moment);
   }
 }
 
