@@ -106,6 +106,28 @@ def lib():
     return _lib
 
 
+_fast = None
+
+
+def fast_lib():
+    """liboracle_fast.so: the same restatement built -O3 -march=native ON THIS HOST (the flags depend on the CPU it runs on, so it
+    is never shipped prebuilt) for the separately reported CPU-throughput figure; results may differ from the parity build in the
+    last bits (FMA contraction).  None if it cannot be built here."""
+    global _fast
+    if _fast is None:
+        path = os.path.join(HERE, "_build", "liboracle_fast.so")
+        try:
+            subprocess.run(["make", "-s", "-B", "-C", HERE, "fast"], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=300)
+            L = C.CDLL(path)
+        except Exception:
+            _fast = False
+            return None
+        _bind_stepping(L)
+        L.orc_handle_collisions.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_double, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]
+        _fast = L
+    return _fast or None
+
+
 def ref_lib():
     """The real vendored nanoflann (oracle/_ref); None if it was never built."""
     global _ref
@@ -338,6 +360,16 @@ class OracleSwarm:
         en, cr, rb = self.collisions
         self._L.orc_handle_collisions(self.h, en, cr, rb, fn, n_threads, _p(pairs), cap, C.byref(cnt))
         return pairs[:min(cnt.value, cap)].copy()
+
+
+class FastOracleSwarm(OracleSwarm):
+    """OracleSwarm on the -O3 -march=native build (throughput figure only, never a parity reference)."""
+
+    def _library(self):
+        L = fast_lib()
+        if L is None:
+            raise RuntimeError("liboracle_fast.so cannot be built on this host")
+        return L
 
 
 class RefSwarm(OracleSwarm):
