@@ -317,6 +317,11 @@ int mrsb_get_counters(mrsb_handle h, int64_t* out5);
  * CTAs, next tile fetched by TMA bulk copies into shared memory); [1] grid size; [2] motors per UAV the kernel was
  * specialised for (0 = per UAV); [3] INPUT_MODE it was specialised for (-1 = per UAV). */
 int mrsb_get_step_info(mrsb_handle h, int32_t* out4);
+/* Diagnostics: device-clock stamps (nanoseconds, %globaltimer) the kernels of the last collision passes left when the handle was
+ * created with the environment variable MRSB_TIMELINE=1: out[k][8] for the last min(n, max_passes, 4096) passes, oldest first —
+ * [0] pass start, [1] peer hand-shake sent, [2] hand-shake complete, [3] halo refresh start, [4] list check start, [5] 1 if the pass
+ * rebuilt its table, [6] unused, [7] list build start.  MRSB_ERR_STATE without the variable. */
+int mrsb_get_timeline(mrsb_handle h, uint64_t* out, int64_t max_passes, int64_t* n_passes);
 /* How the collision pass (SIM:295-359) is organised on this handle: [0] cell edge of the spatial hash in
  * metres, [1] 1 if neighbour lists are kept between table rebuilds (single-shard handles), [2] list
  * radius, [3] skin (the lists survive while twice the accumulated displacement bound stays below it),

@@ -119,6 +119,7 @@ SIGNATURES = {
     "mrsb_set_pair_capacity": (C.c_int, [H, C.c_int64]),
     "mrsb_get_counters": (C.c_int, [H, C.c_void_p]),
     "mrsb_get_step_info": (C.c_int, [H, C.c_void_p]),
+    "mrsb_get_timeline": (C.c_int, [H, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]),
     "mrsb_get_collision_info": (C.c_int, [H, C.c_void_p]),
     "mrsb_forces_written": (C.c_int, [H]),
     "mrsb_nccl_unique_id": (C.c_int, [C.c_void_p]),

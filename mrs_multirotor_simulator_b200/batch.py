@@ -344,6 +344,13 @@ class UavBatch:
         return dict(variant={0: "none", 1: "direct", 2: "staged", 3: "staged+peer-stores"}[int(out[0])], grid=int(out[1]), n_motors=int(out[2]),
                     mode=int(out[3]))
 
+    def timeline(self, max_passes=4096):
+        """Device-clock stamps of the last collision passes [k][8] (needs MRSB_TIMELINE=1 at creation); see mrsb_get_timeline."""
+        out = np.zeros((max_passes, 8), dtype=np.uint64)
+        n = C.c_int64(0)
+        check(self._L.mrsb_get_timeline(self.h, _ptr(out), max_passes, C.byref(n)))
+        return out[:n.value]
+
     def collision_info(self):
         """How the collision pass is organised on this handle (diagnostics; results do not depend on it)."""
         out = np.zeros(8, dtype=np.float64)

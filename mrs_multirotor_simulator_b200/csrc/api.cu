@@ -653,7 +653,7 @@ int mrsb_destroy(mrsb_handle h) {
   void* ptrs[] = {h->ds.st,     h->ds.vprev,  h->ds.rpm,      h->ds.pid,      h->ds.fext,         h->ds.mext,       h->ds.imu,    h->ds.initz,
                   h->ds.cmd,    h->ds.ff,     h->ds.flags,    h->ds.mode,     h->ds.gpos,         h->d_params,      h->d_pset,    h->d_stage,
                   h->d_idx,     h->grid.bucket, h->grid.rank, h->grid.count, h->grid.aabb, h->grid.begin, h->grid.rec, h->grid.pairs,
-                  h->grid.counters, h->grid.scan_state, h->grid.halo_rec, h->grid.halo_bucket, h->grid.halo_rank, h->grid.halo_n,
+                  h->grid.counters, h->grid.tl, h->grid.scan_state, h->grid.halo_rec, h->grid.halo_bucket, h->grid.halo_rank, h->grid.halo_n, h->grid.halo_work,
                   h->grid.nl_count, h->grid.nl_items, h->grid.nl_active, h->grid.ctl};
   for (void* p : ptrs)
     if (p) cudaFree(p);
@@ -801,7 +801,10 @@ int mrsb_create(const mrsb_create_info* info, mrsb_handle* out) {
       CREATE_RC(dalloc(&g.halo_bucket, size_t(g.halo_cap)));
       CREATE_RC(dalloc(&g.halo_rank, size_t(g.halo_cap)));
     }
-    CREATE_RC(dalloc(&g.halo_n, 1));
+    CREATE_RC(dalloc(&g.halo_n, 2));
+    g.halo_work_n = g.halo_n + 1;
+    if (s.n_global > s.n) CREATE_RC(dalloc(&g.halo_work, size_t(g.halo_cap / 32 + MRSB_MAX_RANKS + 1)));
+    if (getenv("MRSB_TIMELINE")) CREATE_RC(dalloc(&g.tl, size_t(MRSB_TL_TICKS) * 8));
     CREATE_RC(dalloc(&g.ctl, 1));
     CREATE_CU(cudaHostAlloc(&h->h_one, 2 * sizeof(uint32_t), cudaHostAllocDefault));
     h->h_one[0] = 1u;
@@ -1116,10 +1119,20 @@ static bool capture_list_pass(mrsb_sim* h, const PassView& v, cudaGraph_t graph,
   if (!*side && cudaStreamCreateWithFlags(side, cudaStreamNonBlocking) != cudaSuccess) return false;
   if (cudaStreamBeginCaptureToGraph(*side, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal) != cudaSuccess) return false;
   *own_rebuild = launch_collide_rebuild(v.s, h->grid, *v.pv, *side);
+  *own_rebuild += launch_collide_check(v.s, h->grid, *v.pv, h->coll_crash, h->coll_rebounce, 0, *side);  // the rebuilding pass' own list check
   cudaGraph_t body_out = nullptr;
   if (cudaStreamEndCapture(*side, &body_out) != cudaSuccess) return false;
-  if (cudaStreamUpdateCaptureDependencies(h->stream, &cond, 1, cudaStreamSetCaptureDependencies) != cudaSuccess) return false;
-  *own_fixed += launch_collide_check(v.s, h->grid, *v.pv, h->coll_crash, h->coll_rebounce, h->stream);
+  // The list check of an ordinary pass is captured BESIDE the conditional node (both depend on decide only): evaluating a
+  // conditional node that is not taken takes ~10 us, which then overlaps the check instead of preceding it.  On a rebuilding
+  // pass this launch returns at once (the body above ends with its own check).  The graph has two leaves; it is complete when
+  // both are.
+  *own_fixed += launch_collide_check(v.s, h->grid, *v.pv, h->coll_crash, h->coll_rebounce, 1, h->stream);
+  cudaGraphNode_t both[2] = {cond, nullptr};
+  const cudaGraphNode_t* tail = nullptr;
+  size_t                 n_tail = 0;
+  if (cudaStreamGetCaptureInfo_v2(h->stream, &status, nullptr, &graph, &tail, &n_tail) != cudaSuccess || n_tail != 1) return false;
+  both[1] = tail[0];
+  if (cudaStreamUpdateCaptureDependencies(h->stream, both, 2, cudaStreamSetCaptureDependencies) != cudaSuccess) return false;
   return true;
 }
 
@@ -1201,7 +1214,7 @@ static int collide_local(mrsb_sim* h) {
       // no graph (MRSB_NO_GRAPH, or conditional nodes unavailable): rebuild every pass
       h->n_launches += launch_collide_decide(h->grid, h->p2pctl, 1, cudaGraphConditionalHandle{}, 0, h->stream);
       h->rebuild_own = launch_collide_rebuild(v.s, h->grid, *v.pv, h->stream);
-      h->n_launches += launch_collide_check(v.s, h->grid, *v.pv, h->coll_crash, h->coll_rebounce, h->stream);
+      h->rebuild_own += launch_collide_check(v.s, h->grid, *v.pv, h->coll_crash, h->coll_rebounce, 0, h->stream);
     }
     return after_pass(h);
   }
@@ -1801,6 +1814,26 @@ int mrsb_get_step_info(mrsb_handle h, int32_t* out4) {
   GUARD(h);
   if (!out4) return fail(MRSB_ERR_INVALID, "null output");
   for (int k = 0; k < 4; k++) out4[k] = h->step_info[k];
+  return MRSB_OK;
+}
+
+int mrsb_get_timeline(mrsb_handle h, uint64_t* out, int64_t max_passes, int64_t* n_passes) {
+  GUARD(h);
+  CU(cudaStreamSynchronize(h->stream));
+  if (n_passes) *n_passes = 0;
+  if (!h->grid.tl) return fail(MRSB_ERR_STATE, "no timeline: set MRSB_TIMELINE=1 before mrsb_create");
+  NlCtl ctl{};
+  CU(cudaMemcpy(&ctl, h->grid.ctl, sizeof(ctl), cudaMemcpyDeviceToHost));
+  const int64_t have = std::min<int64_t>(std::min<int64_t>(int64_t(ctl.n_passes), MRSB_TL_TICKS), max_passes);
+  if (n_passes) *n_passes = have;
+  if (!out || have <= 0) return MRSB_OK;
+  // the last `have` passes, oldest first
+  std::vector<uint64_t> all(size_t(MRSB_TL_TICKS) * 8);
+  CU(cudaMemcpy(all.data(), h->grid.tl, sizeof(uint64_t) * all.size(), cudaMemcpyDeviceToHost));
+  for (int64_t k = 0; k < have; k++) {
+    const uint64_t pass = ctl.n_passes - uint64_t(have) + uint64_t(k);
+    std::memcpy(out + 8 * k, all.data() + (pass % MRSB_TL_TICKS) * 8, sizeof(uint64_t) * 8);
+  }
   return MRSB_OK;
 }
 

@@ -72,6 +72,16 @@ namespace {
 
 #define DEV __device__ __forceinline__
 
+DEV unsigned long long now_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+// timeline stamp of the current pass (diagnostics; g.tl is nullptr in normal operation)
+DEV void stamp(const DevGrid& g, int slot, unsigned long long value) {
+  if (g.tl) g.tl[((g.ctl->n_passes - 1ull) % MRSB_TL_TICKS) * 8 + slot] = value;
+}
+
 DEV int cell_of(double v, double inv_cell) {
   // floor(v / cell): one F2I.FLOOR — saturates to INT_MIN / INT_MAX, NaN -> 0.  Monotone in v, and the
   // SAME function files a record (count_kernel) and looks for it, which is all the stencil needs.
@@ -122,16 +132,8 @@ DEV Geom load_geom(const DevState& s, int64_t gj) {
   g.arm = p[0], g.prop = p[1], g.mass = p[2];
   return g;
 }
-// Remote memory is read with ld.global.cv (fetch again, never from a stale line): the owner rewrites it every tick and the only
-// ordering between the two GPUs is the hand-shake of decide_kernel.  Position and geometry of one remote UAV -> the local cache.
-DEV void fetch_remote(const DevState& s, const PeerView& pv, int r, int64_t gj, double x, double y, double z) {
-  double* lp = s.gpos + 3 * gj;
-  lp[0] = x, lp[1] = y, lp[2] = z;
-  const double2* gp = reinterpret_cast<const double2*>(pv.geom[r] + 4 * gj);
-  const double2  a = __ldcv(gp), b = __ldcv(gp + 1);
-  double2*       lg = reinterpret_cast<double2*>(s.geom + 4 * gj);
-  lg[0] = a, lg[1] = b;
-}
+// Remote memory is always read with ld.global.cv (fetch again, never from a stale line): the owner rewrites it every tick and the
+// only ordering between the two GPUs is the hand-shake of decide_kernel.
 
 // ---- bounding boxes --------------------------------------------------------------------------------
 __global__ void box_reset_kernel(unsigned long long* aabb) {
@@ -219,23 +221,30 @@ __global__ void __launch_bounds__(256) count_kernel(const double* __restrict__ g
 }
 
 // Pull exchange: the remote UAVs that can reach this shard's box, fetched from their owners over NVLink — in as few and as
-// large requests as possible (small remote reads are limited by the number a single SM can keep in flight, not by bandwidth).
-// A warp takes 16 of a peer's 32-UAV groups at a time: their 16 bounding boxes are 96 consecutive words = three coalesced loads;
-// lane g < 16 judges group g.  Only for a group that comes within `reach` of this shard's box are the positions read at all (96
-// consecutive doubles = three coalesced loads, redistributed to one UAV per lane by shuffles), and each UAV is then filtered on
-// its own.  Kept UAVs go to the halo list with their bucket, and their position and geometry into the local cache slots.
-__global__ void __launch_bounds__(256) count_halo_kernel(DevState s, DevGrid g, PeerView pv, uint32_t mask) {
+// large requests as possible, and with as many of them in flight as possible (small remote reads are limited by the number a
+// single SM can keep outstanding, not by bandwidth).  Two kernels:
+//  (1) halo_groups_kernel: a warp takes 16 of a peer's 32-UAV groups at a time — their 16 bounding boxes are 96 consecutive
+//      words = three coalesced loads — and lane g < 16 judges group g; groups that come within `reach` of this shard's box go to
+//      a work list.
+//  (2) halo_fetch_kernel: one warp per listed group: its positions are 96 consecutive doubles = three coalesced loads
+//      (redistributed to one UAV per lane by shuffles), its geometry 128 consecutive doubles; every UAV is then filtered on its
+//      own, and the kept ones go to the halo list with their bucket, and their position and geometry into the local cache slots.
+__global__ void __launch_bounds__(256) halo_groups_kernel(DevGrid g, PeerView pv) {
   const uint32_t full   = 0xffffffffu;
   const int      lane   = threadIdx.x & 31;
   const int64_t  warp   = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int64_t  n_warp = (int64_t(gridDim.x) * blockDim.x) >> 5;
   const double   lo0 = dec(g.aabb[0]) - g.reach, lo1 = dec(g.aabb[1]) - g.reach, lo2 = dec(g.aabb[2]) - g.reach;
   const double   hi0 = dec(g.aabb[3]) + g.reach, hi1 = dec(g.aabb[4]) + g.reach, hi2 = dec(g.aabb[5]) + g.reach;
+  // every (peer, chunk of 16 groups) is one work item; items are dealt to the warps round-robin
+  int64_t item0 = 0;
   for (int r = 0; r < pv.n_ranks; r++) {
     if (r == pv.rank) continue;
-    const int64_t first = pv.begin[r], cnt = pv.begin[r + 1] - first;
-    const int64_t n_grp = (cnt + 31) >> 5, n_words = 6 * n_grp;
-    for (int64_t chunk = warp; chunk * 16 < n_grp; chunk += n_warp) {
+    const int64_t cnt   = pv.begin[r + 1] - pv.begin[r];
+    const int64_t n_grp = (cnt + 31) >> 5, n_words = 6 * n_grp, n_chunk = (n_grp + 15) >> 4;
+    int64_t       chunk = (warp - item0 % n_warp + n_warp) % n_warp;  // the first chunk of this peer that falls to this warp
+    item0 += n_chunk;
+    for (; chunk < n_chunk; chunk += n_warp) {
       uint32_t w[3];
 #pragma unroll
       for (int c = 0; c < 3; c++) {
@@ -250,48 +259,85 @@ __global__ void __launch_bounds__(256) count_halo_kernel(DevState s, DevGrid g, 
       const double b0 = fdec(word(k0)), b1 = fdec(word(k0 + 1)), b2 = fdec(word(k0 + 2));
       const double t0 = fdec(word(k0 + 3)), t1 = fdec(word(k0 + 4)), t2 = fdec(word(k0 + 5));
       const bool   reach = lane < 16 && chunk * 16 + lane < n_grp && !(b0 > hi0 || b1 > hi1 || b2 > hi2 || t0 < lo0 || t1 < lo1 || t2 < lo2);  // NaN bounds: kept
-      for (uint32_t todo = __ballot_sync(full, reach); todo; todo &= todo - 1) {
-        const int64_t grp  = chunk * 16 + (__ffs(int(todo)) - 1);
-        const int64_t l0   = 32 * grp;
-        const int64_t n_d  = 3 * min(int64_t(32), cnt - l0);
-        const double* base = pv.pos[r] + 3 * (first + l0);
-        double        d[3];
-#pragma unroll
-        for (int c = 0; c < 3; c++) d[c] = 32 * c + lane < n_d ? __ldcv(base + 32 * c + lane) : 0.0;
-        auto pick = [&](int k) {
-          const double a = __shfl_sync(full, d[0], k & 31), b = __shfl_sync(full, d[1], k & 31), c = __shfl_sync(full, d[2], k & 31);
-          return k < 32 ? a : (k < 64 ? b : c);
-        };
-        const double x = pick(3 * lane), y = pick(3 * lane + 1), z = pick(3 * lane + 2);
-        if (l0 + lane >= cnt) continue;
-        if (x < lo0 || y < lo1 || z < lo2 || x > hi0 || y > hi1 || z > hi2) continue;
-        const int64_t  gj = first + l0 + lane;
-        const uint32_t bk = bucket_of(x, y, z, g.inv_cell, mask);
-        const uint32_t rk = atomicAdd(&g.count[bk], 1u);
-        if (bk <= 1u) atomicAdd(&g.count[mask + 1u + bk], 1u);
-        const uint32_t slot = atomicAdd(g.halo_n, 1u);
-        if (int64_t(slot) < g.halo_cap) {
-          g.halo_rec[slot]    = make_double4(x, y, z, __longlong_as_double((long long)gj));
-          g.halo_bucket[slot] = bk;
-          g.halo_rank[slot]   = rk;
-        }
-        fetch_remote(s, pv, r, gj, x, y, z);
+      const uint32_t todo = __ballot_sync(full, reach);
+      if (todo) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(g.halo_work_n, uint32_t(__popc(todo)));
+        base = __shfl_sync(full, base, 0);
+        if (reach) g.halo_work[base + __popc(todo & ((1u << lane) - 1u))] = (uint32_t(r) << 26) | uint32_t(chunk * 16 + lane);
       }
     }
+  }
+}
+
+__global__ void __launch_bounds__(256) halo_fetch_kernel(DevState s, DevGrid g, PeerView pv, uint32_t mask) {
+  const uint32_t full   = 0xffffffffu;
+  const int      lane   = threadIdx.x & 31;
+  const int64_t  warp   = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t  n_warp = (int64_t(gridDim.x) * blockDim.x) >> 5;
+  const int64_t  n_work = *g.halo_work_n;
+  const double   lo0 = dec(g.aabb[0]) - g.reach, lo1 = dec(g.aabb[1]) - g.reach, lo2 = dec(g.aabb[2]) - g.reach;
+  const double   hi0 = dec(g.aabb[3]) + g.reach, hi1 = dec(g.aabb[4]) + g.reach, hi2 = dec(g.aabb[5]) + g.reach;
+  for (int64_t item = warp; item < n_work; item += n_warp) {
+    const uint32_t code  = g.halo_work[item];
+    const int      r     = int(code >> 26);
+    const int64_t  grp   = code & 0x3FFFFFFu;
+    const int64_t  first = pv.begin[r], cnt = pv.begin[r + 1] - first;
+    const int64_t  l0    = 32 * grp;
+    const int64_t  n_uav = min(int64_t(32), cnt - l0);
+    const double*  base  = pv.pos[r] + 3 * (first + l0);
+    const double2* gbase = reinterpret_cast<const double2*>(pv.geom[r] + 4 * (first + l0));
+    // every remote load of the group first (positions: 3 coalesced rows; geometry: this lane's UAV): one NVLink round trip
+    double d[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) d[c] = 32 * c + lane < 3 * n_uav ? __ldcv(base + 32 * c + lane) : 0.0;
+    double2 ga = make_double2(0.0, 0.0), gb = ga;
+    if (lane < n_uav) {
+      ga = __ldcv(gbase + 2 * lane);
+      gb = __ldcv(gbase + 2 * lane + 1);
+    }
+    auto pick = [&](int k) {
+      const double a = __shfl_sync(full, d[0], k & 31), b = __shfl_sync(full, d[1], k & 31), c = __shfl_sync(full, d[2], k & 31);
+      return k < 32 ? a : (k < 64 ? b : c);
+    };
+    const double x = pick(3 * lane), y = pick(3 * lane + 1), z = pick(3 * lane + 2);
+    if (lane >= n_uav) continue;
+    if (x < lo0 || y < lo1 || z < lo2 || x > hi0 || y > hi1 || z > hi2) continue;
+    const int64_t  gj = first + l0 + lane;
+    const uint32_t bk = bucket_of(x, y, z, g.inv_cell, mask);
+    const uint32_t rk = atomicAdd(&g.count[bk], 1u);
+    if (bk <= 1u) atomicAdd(&g.count[mask + 1u + bk], 1u);
+    const uint32_t slot = atomicAdd(g.halo_n, 1u);
+    if (int64_t(slot) < g.halo_cap) {
+      g.halo_rec[slot]    = make_double4(x, y, z, __longlong_as_double((long long)gj));
+      g.halo_bucket[slot] = bk;
+      g.halo_rank[slot]   = rk;
+    }
+    double* lp = s.gpos + 3 * gj;
+    lp[0] = x, lp[1] = y, lp[2] = z;
+    double2* lg = reinterpret_cast<double2*>(s.geom + 4 * gj);
+    lg[0] = ga, lg[1] = gb;
   }
 }
 
 // Pull exchange, passes between rebuilds: the CURRENT positions (and geometry) of the halo UAVs of the last rebuild, from their
 // owners into the local cache slots.  A few thousand UAVs; small CTAs so that the remote reads spread over all SMs.
 __global__ void __launch_bounds__(64) refresh_halo_kernel(DevState s, DevGrid g, PeerView pv) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) stamp(g, 3, now_ns());
   if (g.ctl->rebuild) return;  // this pass rebuilds: count_halo_kernel fetches the (new) halo
   const int64_t n = min(int64_t(*g.halo_n), g.halo_cap);
   for (int64_t k = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; k < n; k += int64_t(gridDim.x) * blockDim.x) {
-    const int64_t gj = __double_as_longlong(g.halo_rec[k].w);
-    const int     r  = owner_of(pv, gj);
-    const double* p  = pv.pos[r] + 3 * gj;
+    const int64_t  gj = __double_as_longlong(g.halo_rec[k].w);
+    const int      r  = owner_of(pv, gj);
+    const double*  p  = pv.pos[r] + 3 * gj;
+    const double2* gp = reinterpret_cast<const double2*>(pv.geom[r] + 4 * gj);
+    // all five remote loads first: one NVLink round trip
     const double  x = __ldcv(p), y = __ldcv(p + 1), z = __ldcv(p + 2);
-    fetch_remote(s, pv, r, gj, x, y, z);
+    const double2 a = __ldcv(gp), b = __ldcv(gp + 1);
+    double*       lp = s.gpos + 3 * gj;
+    lp[0] = x, lp[1] = y, lp[2] = z;
+    double2* lg = reinterpret_cast<double2*>(s.geom + 4 * gj);
+    lg[0] = a, lg[1] = b;
   }
 }
 
@@ -591,6 +637,7 @@ __global__ void __launch_bounds__(128, MRSB_COLLIDE_MINB) collide_kernel(DevStat
 // which gives every accepted candidate its list slot without atomics.  A warp handles 8 records, a CTA 32; CTAs stride over the
 // table.  Afterwards lane 0 of the record writes the count word.
 __global__ void __launch_bounds__(128) build_lists_kernel(DevState s, DevGrid g) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) stamp(g, 7, now_ns());
   const uint32_t full  = 0xffffffffu;
   const int      lane  = threadIdx.x & 31;
   const int      k     = threadIdx.x & 3;
@@ -795,7 +842,11 @@ DEV void check_one(const DevState& s, const DevGrid& g, int crash_mode, double r
 }
 
 // A list-only pass: the compacted UAVs that have something to check, grid-stride.
-__global__ void __launch_bounds__(256, 4) check_kernel(DevState s, DevGrid g, int crash_mode, double rebounce) {
+// skip_if_rebuild: this launch runs BESIDE the conditional rebuild node of the graph, not behind it; on a rebuilding pass it does
+// nothing — the rebuild's body ends with its own launch of this kernel.
+__global__ void __launch_bounds__(256, 4) check_kernel(DevState s, DevGrid g, int crash_mode, double rebounce, int skip_if_rebuild) {
+  if (skip_if_rebuild && g.ctl->rebuild) return;
+  if (blockIdx.x == 0 && threadIdx.x == 0) stamp(g, 4, now_ns());
   const uint32_t n_active = g.ctl->n_active;
   for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n_active; k += gridDim.x * blockDim.x) check_one(s, g, crash_mode, rebounce, g.nl_active[k]);
 }
@@ -810,9 +861,11 @@ __global__ void __launch_bounds__(256, 4) check_kernel(DevState s, DevGrid g, in
 //  (2) Are the neighbour lists still good for the positions of this pass?  The swarm-wide displacement bound is the largest of
 //      every rank's; everything else is as on a single GPU.
 __global__ void __launch_bounds__(32) decide_kernel(NlCtl* __restrict__ c, unsigned long long* __restrict__ pair_counter, double skin, int always,
-                                                    cudaGraphConditionalHandle handle, int has_handle, P2PCtl p) {
+                                                    cudaGraphConditionalHandle handle, int has_handle, P2PCtl p, unsigned long long* tl) {
   const uint32_t full = 0xffffffffu;
   const int      lane = threadIdx.x;
+  unsigned long long* row = tl ? tl + (c->n_passes % MRSB_TL_TICKS) * 8 : nullptr;
+  if (row && lane == 0) row[0] = now_ns();
   // every load first (they are independent: one round trip), then the decision, then the stores
   uint32_t                 bits  = c->disp_max_bits;  // largest squared displacement of the stepping launch since the last pass (float, rounded up)
   const double             D_old = c->D_total;
@@ -826,6 +879,7 @@ __global__ void __launch_bounds__(32) decide_kernel(NlCtl* __restrict__ c, unsig
     if (peer) theirs[p.n_ranks + 2 * p.rank + slot] = (unsigned long long)(always ? 0xFFFFFFFFu : bits);  // a rank without lists cannot bound its displacement
     __threadfence_system();
     if (peer) theirs[p.rank] = epoch;
+    if (row && lane == 0) row[1] = now_ns();
     uint32_t got = 0u;
     if (peer) {
       volatile const unsigned long long* mine = p.flags;
@@ -846,6 +900,7 @@ __global__ void __launch_bounds__(32) decide_kernel(NlCtl* __restrict__ c, unsig
     if (lane == 0) c->epoch = epoch;
   }
   if (lane != 0) return;
+  if (row) row[2] = now_ns();
   const double d       = __dsqrt_ru(double(__uint_as_float(bits)));  // NaN stays NaN
   double       D       = __dadd_ru(D_old, d);
   const bool   rebuild = always || force || !valid || !(__dmul_ru(2.0, D) <= skin);
@@ -860,6 +915,7 @@ __global__ void __launch_bounds__(32) decide_kernel(NlCtl* __restrict__ c, unsig
     c->n_active  = 0u;  // ... and compact_kernel the UAVs with work
     c->n_rebuilds = n_rebuilds + 1ull;
   }
+  if (row) row[5] = rebuild ? 1ull : 0ull;
   c->D_total  = D;
   c->rebuild  = rebuild ? 1u : 0u;
   c->n_passes = n_passes + 1ull;
@@ -889,7 +945,7 @@ static int launch_table(const DevState& s, const DevGrid& g, const PeerView& pv,
     own += 2;
   }
   if (pull) {
-    cudaMemsetAsync(g.halo_n, 0, sizeof(uint32_t), stream);
+    cudaMemsetAsync(g.halo_n, 0, 2 * sizeof(uint32_t), stream);  // halo_n and the work-list counter behind it
     box_reset_kernel<<<1, 32, 0, stream>>>(g.aabb);
     const int64_t n_groups = (s.n + 31) / 32;
     if (n_groups > 0) box_from_groups_kernel<<<unsigned(std::min<int64_t>((n_groups + 255) / 256, 148)), 256, 0, stream>>>(s.gbox, n_groups, g.aabb);
@@ -900,12 +956,13 @@ static int launch_table(const DevState& s, const DevGrid& g, const PeerView& pv,
     own += 1;
   }
   if (pull) {
-    int64_t groups = 0;
+    int64_t chunks = 0;
     for (int r = 0; r < pv.n_ranks; r++)
-      if (r != pv.rank) groups = std::max(groups, (pv.begin[r + 1] - pv.begin[r] + 31) / 32);
-    if (groups > 0) {
-      count_halo_kernel<<<unsigned(std::min<int64_t>((groups + 127) / 128, 148 * 4)), T, 0, stream>>>(s, g, pv, g.n_buckets - 1);  // 16 groups per warp
-      own += 1;
+      if (r != pv.rank) chunks += ((pv.begin[r + 1] - pv.begin[r] + 31) / 32 + 15) / 16;
+    if (chunks > 0) {
+      halo_groups_kernel<<<unsigned(std::min<int64_t>((chunks + 7) / 8, 148 * 4)), T, 0, stream>>>(g, pv);
+      halo_fetch_kernel<<<148 * 2, T, 0, stream>>>(s, g, pv, g.n_buckets - 1);  // one warp per listed group, grid-stride over the list
+      own += 2;
     }
   }
   scan_kernel<false><<<unsigned(g.scan_tiles), 256, 0, stream>>>(g.count, g.begin, n_scan, g.scan_state);
@@ -940,7 +997,7 @@ int launch_collide(const DevState& s, const DevGrid& g, const PeerView& pv, cons
 // ---- the pass with neighbour lists, in three pieces so that api.cu can put the middle one into the
 // body of a conditional graph node -----------------------------------------------------------------
 int launch_collide_decide(const DevGrid& g, const P2PCtl& p2p, int always, cudaGraphConditionalHandle handle, int has_handle, cudaStream_t stream) {
-  decide_kernel<<<1, 32, 0, stream>>>(g.ctl, g.counters, g.skin, always, handle, has_handle, p2p);
+  decide_kernel<<<1, 32, 0, stream>>>(g.ctl, g.counters, g.skin, always, handle, has_handle, p2p, g.tl);
   return 1;
 }
 int launch_collide_rebuild(const DevState& s, const DevGrid& g, const PeerView& pv, cudaStream_t stream) {
@@ -954,14 +1011,15 @@ int launch_collide_rebuild(const DevState& s, const DevGrid& g, const PeerView& 
   compact_kernel<<<unsigned((s.n + 255) / 256), 256, 0, stream>>>(g, g.rank, s.n);
   return own + 3;
 }
-int launch_collide_check(const DevState& s, const DevGrid& g, const PeerView& pv, int crash_mode, double rebounce, cudaStream_t stream) {
+// list check.  beside_rebuild: captured next to the conditional node (see check_kernel); it then also refreshes the halo first.
+int launch_collide_check(const DevState& s, const DevGrid& g, const PeerView& pv, int crash_mode, double rebounce, int beside_rebuild, cudaStream_t stream) {
   if (s.n <= 0) return 0;
   int own = 0;
-  if (pv.n_ranks > 1) {
+  if (pv.n_ranks > 1 && beside_rebuild) {
     // between rebuilds: the halo's current positions from their owners (a rebuild fetches them itself)
     refresh_halo_kernel<<<unsigned(std::max<int64_t>(1, std::min<int64_t>((g.halo_cap + 63) / 64, 148 * 2))), 64, 0, stream>>>(s, g, pv);
     own += 1;
   }
-  check_kernel<<<unsigned(std::min<int64_t>((s.n + 255) / 256, 148 * 4)), 256, 0, stream>>>(s, g, crash_mode, rebounce);
+  check_kernel<<<unsigned(std::min<int64_t>((s.n + 255) / 256, 148 * 4)), 256, 0, stream>>>(s, g, crash_mode, rebounce, beside_rebuild);
   return own + 1;
 }

@@ -130,6 +130,7 @@ struct P2PCtl {
 
 // neighbour lists (collide.cu): candidates per UAV kept between table rebuilds
 #define MRSB_NL_CAP 8
+#define MRSB_TL_TICKS 4096
 struct NlCtl {
   uint32_t disp_max_bits;  // written by the stepping kernel (DevState::disp_max points here)
   uint32_t force;          // host: positions changed behind the stepping kernel's back -> rebuild
@@ -166,8 +167,13 @@ struct DevGrid {
   // pull exchange: remote UAVs that can reach this shard's box, fetched from their owners at a rebuild
   double4*  halo_rec;   // [halo_cap] {x, y, z, global index}
   uint32_t* halo_bucket, *halo_rank;  // [halo_cap]
-  uint32_t* halo_n;     // device counter
+  uint32_t* halo_n;     // device counter; halo_n[1] = halo_work_n
+  uint32_t* halo_work;  // [groups of all peers] work list of a rebuild: (rank << 26 | group) of the remote 32-UAV groups that can reach this shard
+  uint32_t* halo_work_n;
   int64_t   halo_cap;
+  // diagnostics (MRSB_TIMELINE=1 at create): %globaltimer stamps of the pass' kernels, [MRSB_TL_TICKS][8] indexed by pass number:
+  // 0 decide start, 1 hand-shake sent, 2 hand-shake complete, 3 halo refresh start, 4 list check start, 5 rebuild flag, 6 table build start, 7 list build start
+  unsigned long long* tl;
   int32_t*  pairs;      // [pair_cap][2]
   int64_t   pair_cap;
   unsigned long long* counters;  // [0] pairs found by the last pass
@@ -186,7 +192,7 @@ int launch_collide(const DevState& s, const DevGrid& g, const PeerView& pv, cons
 // the pass with neighbour lists: decide (always; includes the peer hand-shake) | rebuild (body of the graph's conditional node) | check (always)
 int launch_collide_decide(const DevGrid& g, const P2PCtl& p2p, int always, cudaGraphConditionalHandle handle, int has_handle, cudaStream_t stream);
 int launch_collide_rebuild(const DevState& s, const DevGrid& g, const PeerView& pv, cudaStream_t stream);
-int launch_collide_check(const DevState& s, const DevGrid& g, const PeerView& pv, int crash_mode, double rebounce, cudaStream_t stream);
+int launch_collide_check(const DevState& s, const DevGrid& g, const PeerView& pv, int crash_mode, double rebounce, int beside_rebuild, cudaStream_t stream);
 int scan_tiles_for(int64_t n_items);
 int launch_publish_positions(const DevState& s, cudaStream_t stream);
 

@@ -69,6 +69,19 @@ else:
     out.update({"tick_us": total, "step_us_median": float(np.median(step)), "pass_us_median": float(np.median(coll)), "pass_us_p90": float(np.quantile(coll, 0.9)),
                 "pass_us_mean": float(coll.mean()), "pass_us_mean_of_rebuild_ticks": float(order[-k:].mean()), "pass_us_mean_of_list_ticks": float(order[:-k].mean()),
                 "rebuild_fraction": (i1["rebuilds"] - i0["rebuilds"]) / ticks, "pairs_last": b.counters()["pairs"]})
+if os.environ.get("MRSB_TIMELINE"):
+    tl = b.timeline(ticks).astype(np.int64)
+    if len(tl) > 10:
+        lst = tl[tl[:, 5] == 0]
+        d = lambda a: float(np.median(a)) / 1000.0
+        nxt = tl[1:, 0] - tl[:-1, 4]
+        keep = tl[:-1, 5] == 0
+        out["timeline_us_list_ticks"] = {"signal": d(lst[:, 1] - lst[:, 0]), "wait_for_peers": d(lst[:, 2] - lst[:, 1]), "decide_to_refresh": d(lst[:, 3] - lst[:, 2]),
+                                         "refresh_to_check": d(lst[:, 4] - lst[:, 3]), "check_start_to_next_pass_start(check+step+gaps)": d(nxt[keep]),
+                                         "pass_start_period": d(tl[1:, 0] - tl[:-1, 0])}
+        reb = tl[tl[:, 5] == 1]
+        if len(reb):
+            out["timeline_us_rebuild_ticks"] = {"decide_to_list_build": d(reb[:, 7] - reb[:, 2]), "list_build_to_check": d(reb[:, 4] - reb[:, 7]), "n": int(len(reb))}
 if world > 1:
     res = [None] * world
     dist.all_gather_object(res, out)
