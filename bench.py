@@ -497,20 +497,23 @@ def run_b200(args):
         tou = (np.arange(N_UAVS) % 3).astype(np.int32)
         spawn, _ = workload(begin, n_local)
         b5 = UavBatch(types, type_of_uav=tou, spawn_xyz=spawn, n=n_local, device=local, n_global=N_UAVS, shard_begin=begin)
+        b5.set_outputs(imu=True, positions=False)  # nothing consumes packed positions here: no collision pass, no position download
         st5 = torch.cuda.ExternalStream(b5.stream, device=dev)
         k = np.arange(begin, begin + n_local)
-        draws = [np.ascontiguousarray(np.stack([0.4 + 0.3 * u01(SEED + d, 10 + m, k) for m in range(8)], axis=1)) for d in range(2)]
-        b5.set_input(ACTUATOR_CMD, draws[0])
+        # the two alternating command draws live on the device (an RL policy would produce them there): re-drawing = one
+        # device-side scatter through mrsb_set_input_device, inside the timed region
+        draws = [torch.from_numpy(np.ascontiguousarray(np.stack([0.4 + 0.3 * u01(SEED + d, 10 + m, k) for m in range(8)], axis=1))).to(dev) for d in range(2)]
+        torch.cuda.synchronize()
+        b5.set_input_device(ACTUATOR_CMD, draws[0].data_ptr(), 8)
         for _ in range(5):
             b5.make_step(DT)
         c5_steps = min(max(args.steps, 100), 200)
-
         c5_tick = [0]
 
         def c5_block(n):
             for _ in range(n):
                 if c5_tick[0] % 100 == 0:
-                    b5.set_input(ACTUATOR_CMD, draws[(c5_tick[0] // 100) & 1])
+                    b5.set_input_device(ACTUATOR_CMD, draws[(c5_tick[0] // 100) & 1].data_ptr(), 8)
                 b5.make_step(DT)
                 c5_tick[0] += 1
 

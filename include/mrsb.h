@@ -359,8 +359,11 @@ int mrsb_handle_collisions_gathered(mrsb_handle h);
 
 /* ---- zero-copy access for device-resident callers (RL loops) -------------------------------
  * Device pointers into the library's tiled structure-of-arrays state.  Every per-UAV array is cut
- * into tiles of `tile` (=128) consecutive UAVs; component c of UAV i of an array with R rows is at
- *     ptr[((i / tile) * R + c) * tile + i % tile].
+ * into tiles of `tile` (=128) consecutive SLOTS; component c of the UAV in slot s of an array with R rows is at
+ *     ptr[((s / tile) * R + c) * tile + s % tile].
+ * A batch with one airframe type keeps UAV i in slot i (slot_of_uav == NULL).  A batch created with several types is
+ * bucketed by type (every tile then holds one airframe, so the specialised kernels run): slot_of_uav[i] is the slot of
+ * UAV i (device array of n_local int32).
  * state: R = state_rows = 18 (x 0-2, v 3-5, R column-major 6-14, omega 15-17 — the reference's
  * InternalState order, MM:204-214); motor_rpm: R = MRSB_MAX_MOTORS; imu_acc, ext_force: R = 3.
  * flags[i] bit 0 = crashed; input_mode[i] = INPUT_MODE.  Valid until mrsb_destroy. */
@@ -373,6 +376,7 @@ typedef struct mrsb_device_view {
   double*   ext_force;
   uint32_t* flags;
   uint8_t*  input_mode;
+  const int32_t* slot_of_uav; /* NULL = identity */
 } mrsb_device_view;
 int mrsb_get_device_view(mrsb_handle h, mrsb_device_view* out);
 /* After writing through the view: positions (state rows 0-2) -> mrsb_publish_positions, so that the

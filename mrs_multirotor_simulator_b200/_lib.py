@@ -40,7 +40,7 @@ class CreateInfo(C.Structure):
 
 class DeviceView(C.Structure):
     _fields_ = [("tile", C.c_int32), ("state_rows", C.c_int32), ("state", C.c_void_p), ("motor_rpm", C.c_void_p), ("imu_acc", C.c_void_p),
-                ("ext_force", C.c_void_p), ("flags", C.c_void_p), ("input_mode", C.c_void_p)]
+                ("ext_force", C.c_void_p), ("flags", C.c_void_p), ("input_mode", C.c_void_p), ("slot_of_uav", C.c_void_p)]
 
 
 # every symbol include/mrsb.h declares: name -> (restype, argtypes)

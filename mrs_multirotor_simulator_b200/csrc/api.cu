@@ -110,10 +110,19 @@ struct mrsb_sim {
   size_t   d_idx_cap     = 0;
 
   int  uniform_mode = MRSB_INPUT_UNKNOWN;  // INPUT_MODE shared by all UAVs, or -1 if mixed
-  int  uniform_nm   = 0;                   // n_motors shared by all local UAVs, or 0 if mixed
-  int  uniform_pset = -1;                  // parameter set shared by all local UAVs, or -1 if mixed
-  DevParams uniform_params{};              // host copy of that set (goes to the kernel by value)
   bool any_moment   = false;
+  // Buckets of the tiled arrays: one per airframe type present at create (a single one for a uniform batch), each a whole number
+  // of tiles, so that the stepping kernel specialised for (motor count, parameter set) runs on each.
+  struct Bucket {
+    int64_t   slot0 = 0, count = 0;  // first slot (multiple of 128), UAVs
+    int       nm    = 0;             // n_motors shared by its UAVs, or 0 if mixed (after per-UAV setParams)
+    int       pset  = -1;            // parameter set shared by its UAVs, or -1 if mixed
+    DevParams params{};              // host copy of that set (goes to the staged kernel by value)
+  };
+  std::vector<Bucket>  buckets;
+  std::vector<int32_t> perm_host, inv_host;  // external local index -> slot, slot -> external (-1 = padding); empty = identity
+  int32_t*             d_perm = nullptr;
+  int32_t*             d_inv  = nullptr;
 
   int    coll_enabled = 0, coll_crash = 0;
   double coll_rebounce = 0.0;
@@ -171,7 +180,8 @@ struct mrsb_sim {
   uint32_t* h_one              = nullptr;  // pinned constant 1 (source of the async "force rebuild" copy)
   cudaGraphExec_t tick_graph[2] = {nullptr, nullptr};  // mrsb_run: stepping launch + collision pass as ONE graph per parity
   double   tick_dt = 0.0;
-  int      tick_k = 0, tick_mode = -2, tick_nm = -1, tick_pset = -2, tick_own[2] = {0, 0};
+  int      tick_k = 0, tick_mode = -2, tick_own[2] = {0, 0};
+  uint64_t tick_pset = ~0ull;  // fingerprint of the buckets' parameter sets the graphs were built for
   uint32_t tick_opts = 0;
   bool     tick_failed = false;
 
@@ -250,7 +260,7 @@ static int collect_param_sets(mrsb_sim* h) {
     kept.push_back(h->sets[size_t(k)]);
   }
   h->sets.swap(kept);
-  h->tick_pset = -2;  // ids mean something else now
+  h->tick_pset = ~0ull;  // ids mean something else now
   for (int32_t& id : h->pset_host) id = remap[size_t(id)];
   CU(cudaMemcpyAsync(h->d_pset, h->pset_host.data(), sizeof(int32_t) * h->pset_host.size(), cudaMemcpyHostToDevice, h->stream));
   CU(cudaStreamSynchronize(h->stream));
@@ -276,19 +286,22 @@ static int flush_params(mrsb_sim* h) {
   CU(cudaMemcpyAsync(h->d_params, host.data(), sizeof(DevParams) * n_sets, cudaMemcpyHostToDevice, h->stream));
   CU(cudaStreamSynchronize(h->stream));  // `host` goes out of scope
   h->filt_dt = -1.0;                     // DevParams::filt has to be prepared again (ensure_filt)
-  int nm = -1, ps = -2;
-  for (int64_t i = 0; i < h->ds.n; i++) {
-    const int id = h->pset_host[h->ds.shard_begin + i];
-    const int m  = h->sets[id].mp.n_motors;
-    if (nm == -1) nm = m;
-    if (nm != m) nm = 0;
-    if (ps == -2) ps = id;
-    if (ps != id) ps = -1;
-    if (nm == 0 && ps == -1) break;
+  for (mrsb_sim::Bucket& b : h->buckets) {
+    int nm = -1, ps = -2;
+    for (int64_t k = 0; k < b.count; k++) {
+      const int64_t e  = h->inv_host.empty() ? b.slot0 + k : h->inv_host[size_t(b.slot0 + k)];
+      const int     id = h->pset_host[size_t(h->ds.shard_begin + e)];
+      const int     m  = h->sets[size_t(id)].mp.n_motors;
+      if (nm == -1) nm = m;
+      if (nm != m) nm = 0;
+      if (ps == -2) ps = id;
+      if (ps != id) ps = -1;
+      if (nm == 0 && ps == -1) break;
+    }
+    b.nm   = nm > 0 ? nm : 0;
+    b.pset = ps >= 0 ? ps : -1;
+    if (b.pset >= 0) b.params = host[size_t(b.pset)];
   }
-  h->uniform_nm   = nm > 0 ? nm : 0;
-  h->uniform_pset = ps >= 0 ? ps : -1;
-  if (h->uniform_pset >= 0) h->uniform_params = host[size_t(h->uniform_pset)];
   h->params_dirty = false;
   return MRSB_OK;
 }
@@ -298,8 +311,8 @@ static int flush_params(mrsb_sim* h) {
 static int ensure_filt(mrsb_sim* h, double dt) {
   if (h->filt_dt == dt) return MRSB_OK;
   h->n_launches += launch_prep_params(h->d_params, int(h->sets.size()), dt, h->stream);
-  if (h->uniform_pset >= 0)
-    CU(cudaMemcpyAsync(&h->uniform_params.filt, &h->d_params[h->uniform_pset].filt, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  for (mrsb_sim::Bucket& b : h->buckets)
+    if (b.pset >= 0) CU(cudaMemcpyAsync(&b.params.filt, &h->d_params[b.pset].filt, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   h->filt_dt = dt;
   for (int k = 0; k < 2; k++) {  // the tick graphs hold the parameter set by value
@@ -506,7 +519,7 @@ static int setup_p2p(mrsb_sim* h) {
   const int    G     = h->n_ranks;
   const size_t bytes = sizeof(double) * 3 * size_t(h->ds.n_global);
   const size_t gbytes = sizeof(double) * 4 * size_t(h->ds.n_global);
-  const size_t bbytes = sizeof(uint32_t) * 6 * size_t(h->ds.ld / 32);
+  const size_t bbytes = sizeof(uint32_t) * 6 * size_t(h->ds.ld / 32 + 1);  // the stepping kernel writes one row per warp of every tile
   h->gbuf[0]          = h->ds.gpos;
   CU(cudaMalloc(&h->gbuf[1], std::max<size_t>(bytes, 16)));
   CU(cudaMemcpy(h->gbuf[1], h->gbuf[0], bytes, cudaMemcpyDeviceToDevice));
@@ -645,7 +658,7 @@ int mrsb_destroy(mrsb_handle h) {
     for (int k = 0; k < 2; k++)
       if (h->gbuf[k]) cudaFree(h->gbuf[k]);
   }
-  for (void* p : {(void*)h->d_geom[0], (void*)h->d_geom[1], (void*)h->d_gbox[0], (void*)h->d_gbox[1], (void*)h->d_flags, (void*)h->d_peer_flags})
+  for (void* p : {(void*)h->d_perm, (void*)h->d_inv, (void*)h->d_geom[0], (void*)h->d_geom[1], (void*)h->d_gbox[0], (void*)h->d_gbox[1], (void*)h->d_flags, (void*)h->d_peer_flags})
     if (p) cudaFree(p);
   if (h->h_status) cudaFreeHost(h->h_status);
   if (h->h_one) cudaFreeHost(h->h_one);
@@ -705,10 +718,59 @@ int mrsb_create(const mrsb_create_info* info, mrsb_handle* out) {
 
   DevState& s   = h->ds;
   s.n           = info->n_local;
-  s.ld          = std::max<int64_t>(128, round_up(info->n_local, 128));
   s.n_global    = info->n_global;
   s.shard_begin = info->shard_begin;
+  s.n_groups32  = (s.n + 31) / 32;
+  // Buckets: the local UAVs sorted (stably) by airframe type, every type padded to whole 128-UAV tiles, when the batch has
+  // between 2 and 8 types (more: one bucket, generic kernel).  MRSB_NO_BUCKETS=1 keeps the external order.
+  {
+    std::vector<int64_t> per_type(size_t(info->n_types), 0);
+    for (int64_t i = 0; i < s.n; i++) {
+      const int t = info->type_of_uav ? info->type_of_uav[s.shard_begin + i] : 0;
+      if (t < 0 || t >= info->n_types) {
+        mrsb_destroy(h);
+        return fail(MRSB_ERR_INVALID, "type_of_uav[%lld]=%d outside 0..%d", (long long)(s.shard_begin + i), t, info->n_types - 1);
+      }
+      per_type[size_t(t)]++;
+    }
+    int present = 0;
+    for (int64_t c : per_type) present += c > 0;
+    if (present >= 2 && present <= 8 && !getenv("MRSB_NO_BUCKETS")) {
+      std::vector<int64_t> next(size_t(info->n_types), 0);
+      int64_t              slot = 0;
+      for (int t = 0; t < info->n_types; t++) {
+        if (!per_type[size_t(t)]) continue;
+        mrsb_sim::Bucket b;
+        b.slot0 = slot, b.count = per_type[size_t(t)];
+        h->buckets.push_back(b);
+        next[size_t(t)] = slot;
+        slot += round_up(b.count, MRSB_TILE);
+      }
+      s.ld = slot;
+      h->perm_host.assign(size_t(s.n), 0);
+      h->inv_host.assign(size_t(s.ld), -1);
+      for (int64_t i = 0; i < s.n; i++) {
+        const int t                     = info->type_of_uav[s.shard_begin + i];
+        const int64_t sl                = next[size_t(t)]++;
+        h->perm_host[size_t(i)]         = int32_t(sl);
+        h->inv_host[size_t(sl)]         = int32_t(i);
+      }
+    } else {
+      mrsb_sim::Bucket b;
+      b.slot0 = 0, b.count = s.n;
+      h->buckets.push_back(b);
+      s.ld = std::max<int64_t>(128, round_up(info->n_local, 128));
+    }
+  }
   const size_t ld = size_t(s.ld);
+  if (!h->perm_host.empty()) {
+    CREATE_RC(dalloc(&h->d_perm, size_t(s.n)));
+    CREATE_RC(dalloc(&h->d_inv, ld));
+    CREATE_CU(cudaMemcpy(h->d_perm, h->perm_host.data(), sizeof(int32_t) * size_t(s.n), cudaMemcpyHostToDevice));
+    CREATE_CU(cudaMemcpy(h->d_inv, h->inv_host.data(), sizeof(int32_t) * ld, cudaMemcpyHostToDevice));
+    s.perm = h->d_perm;
+    s.inv  = h->d_inv;
+  }
   CREATE_RC(dalloc(&s.st, 18 * ld));
   CREATE_RC(dalloc(&s.vprev, 3 * ld));
   CREATE_RC(dalloc(&s.rpm, MRSB_NM * ld));
@@ -751,7 +813,8 @@ int mrsb_create(const mrsb_create_info* info, mrsb_handle* out) {
   {
     std::vector<uint32_t> fl(ld, 0u);
     for (int64_t i = 0; i < s.n; i++)
-      fl[size_t(i)] = h->sets[h->pset_host[size_t(s.shard_begin + i)]].mp.takeoff_patch_enabled ? FLAG_TAKEOFF : 0u;
+      fl[h->perm_host.empty() ? size_t(i) : size_t(h->perm_host[size_t(i)])] =
+          h->sets[h->pset_host[size_t(s.shard_begin + i)]].mp.takeoff_patch_enabled ? FLAG_TAKEOFF : 0u;
     CREATE_CU(cudaMemcpy(s.flags, fl.data(), sizeof(uint32_t) * ld, cudaMemcpyHostToDevice));
     const size_t bytes = sizeof(double) * 4 * size_t(std::max<int64_t>(s.n, 1));
     CREATE_RC(ensure_stage(h, bytes));
@@ -995,7 +1058,7 @@ static int put_rows(mrsb_sim* h, double* dst, int rows_total, int row0, int rows
   rc                 = ensure_stage(h, bytes);
   if (rc) return rc;
   CU(cudaMemcpyAsync(h->d_stage, payload, bytes, cudaMemcpyHostToDevice, h->stream));
-  h->n_launches += launch_scatter_rows(dst, rows_total, row0, rows, n, d_idx, reinterpret_cast<const double*>(h->d_stage), stride, h->stream);
+  h->n_launches += launch_scatter_rows(dst, rows_total, row0, rows, n, d_idx, reinterpret_cast<const double*>(h->d_stage), stride, h->ds.perm, h->stream);
   if (or_flag) h->n_launches += launch_flag_update(h->ds, n, d_idx, 0xffffffffu, or_flag, h->stream);
   CU(cudaGetLastError());
   return MRSB_OK;
@@ -1009,7 +1072,7 @@ static int get_rows(mrsb_sim* h, const double* src, int rows_total, int row0, in
   const size_t bytes = sizeof(double) * size_t(n) * size_t(rows);
   rc                 = ensure_stage(h, bytes);
   if (rc) return rc;
-  h->n_launches += launch_gather_rows(src, rows_total, row0, rows, n, d_idx, reinterpret_cast<double*>(h->d_stage), rows, h->stream);
+  h->n_launches += launch_gather_rows(src, rows_total, row0, rows, n, d_idx, reinterpret_cast<double*>(h->d_stage), rows, h->ds.perm, h->stream);
   CU(cudaMemcpyAsync(out, h->d_stage, bytes, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   return MRSB_OK;
@@ -1075,6 +1138,8 @@ static int exchange_positions(mrsb_sim* h) {
   }
   return MRSB_OK;
 }
+
+static int launch_step_buckets(mrsb_sim* h, double dt, int k_substeps);
 
 // what the kernels of the collision pass that comes next read: with the pull exchange, the buffers of that pass' parity
 struct PassView {
@@ -1150,9 +1215,7 @@ static cudaGraphExec_t build_pass_graph(mrsb_sim* h, const PassView& v, bool wit
   do {
     cudaStreamCaptureStatus status;
     if (cudaStreamGetCaptureInfo_v2(h->stream, &status, nullptr, &graph, nullptr, nullptr) != cudaSuccess || !graph) break;
-    if (with_step)
-      *own_fixed += launch_step(h->ds, h->uniform_pset >= 0 ? &h->uniform_params : nullptr, dt, k_sub, h->uniform_mode, h->uniform_nm, h->any_moment, h->stream,
-                                h->step_info);
+    if (with_step) *own_fixed += launch_step_buckets(h, dt, k_sub);
     ok = capture_list_pass(h, v, graph, &side, own_fixed, own_rebuild);
   } while (false);
   cudaGraph_t captured = nullptr;
@@ -1240,6 +1303,35 @@ static int collide_local(mrsb_sim* h) {
   return after_pass(h);
 }
 
+// the stepping launch: one kernel per bucket, each on its own view of the tiled arrays
+static int launch_step_buckets(mrsb_sim* h, double dt, int k_substeps) {
+  int own = 0;
+  for (const mrsb_sim::Bucket& b : h->buckets) {
+    if (b.count <= 0) continue;
+    DevState v = h->ds;
+    if (b.slot0 > 0) {
+      const int64_t t0 = b.slot0 / MRSB_TILE;
+      v.st += t0 * ST_ROWS * MRSB_TILE, v.vprev += t0 * VPREV_ROWS * MRSB_TILE, v.rpm += t0 * MRSB_NM * MRSB_TILE, v.pid += t0 * PID_ROWS * MRSB_TILE;
+      v.fext += t0 * F3_ROWS * MRSB_TILE, v.mext += t0 * F3_ROWS * MRSB_TILE, v.imu += t0 * F3_ROWS * MRSB_TILE, v.cmd += t0 * CMD_ROWS * MRSB_TILE;
+      v.ff += t0 * FF_ROWS * MRSB_TILE, v.initz += b.slot0, v.flags += b.slot0, v.mode += b.slot0;
+    }
+    if (v.inv) {
+      v.inv += b.slot0;
+      v.gbox = nullptr;  // its warps are not the external 32-UAV groups: publish_positions_kernel writes the boxes (below)
+    }
+    v.n = b.count;
+    own += launch_step(v, b.pset >= 0 ? &b.params : nullptr, dt, k_substeps, h->uniform_mode, b.nm, h->any_moment, h->stream, h->step_info);
+  }
+  if (h->p2p && h->ds.perm) own += launch_publish_positions(h->ds, h->stream);  // bucketed: the per-group boxes follow the EXTERNAL order
+  return own;
+}
+
+static uint64_t bucket_fingerprint(const mrsb_sim* h) {
+  uint64_t f = 1469598103934665603ull;
+  for (const mrsb_sim::Bucket& b : h->buckets) f = (f ^ uint64_t(uint32_t(b.pset + 1) * 16u + uint32_t(b.nm))) * 1099511628211ull;
+  return f;
+}
+
 static int before_step(mrsb_sim* h, double dt, int32_t k_substeps) {
   if (k_substeps < 1) return fail(MRSB_ERR_INVALID, "k_substeps must be >= 1");
   int rc = flush_params(h);
@@ -1254,8 +1346,7 @@ int mrsb_make_step(mrsb_handle h, double dt, int32_t k_substeps) {
   GUARD(h);
   int rc = before_step(h, dt, k_substeps);
   if (rc) return rc;
-  h->n_launches += launch_step(h->ds, h->uniform_pset >= 0 ? &h->uniform_params : nullptr, dt, k_substeps, h->uniform_mode, h->uniform_nm,
-                               h->any_moment, h->stream, h->step_info);
+  h->n_launches += launch_step_buckets(h, dt, k_substeps);
   h->wrote_since_pass = true;
   h->n_steps += k_substeps;
   h->steps_since_pass++;
@@ -1299,13 +1390,13 @@ static int run_tick_graph(mrsb_sim* h, double dt, int32_t k_substeps, bool* done
   *done = false;
   if (!h->lists_on || h->tick_failed || h->list_graph_failed || getenv("MRSB_NO_GRAPH") || getenv("MRSB_NO_TICK_GRAPH")) return MRSB_OK;
   if (h->positions_touched || h->steps_since_pass != 0) return MRSB_OK;  // let the ordinary path sort that out first
-  if (h->tick_dt != dt || h->tick_k != k_substeps || h->tick_mode != h->uniform_mode || h->tick_nm != h->uniform_nm || h->tick_pset != h->uniform_pset ||
+  if (h->tick_dt != dt || h->tick_k != k_substeps || h->tick_mode != h->uniform_mode || h->tick_pset != bucket_fingerprint(h) ||
       h->tick_opts != (h->ds.opts | (h->any_moment ? 0x10000u : 0u))) {
     for (int k = 0; k < 2; k++) {
       if (h->tick_graph[k]) cudaGraphExecDestroy(h->tick_graph[k]);
       h->tick_graph[k] = nullptr;
     }
-    h->tick_dt = dt, h->tick_k = k_substeps, h->tick_mode = h->uniform_mode, h->tick_nm = h->uniform_nm, h->tick_pset = h->uniform_pset,
+    h->tick_dt = dt, h->tick_k = k_substeps, h->tick_mode = h->uniform_mode, h->tick_pset = bucket_fingerprint(h),
     h->tick_opts = h->ds.opts | (h->any_moment ? 0x10000u : 0u);
     return MRSB_OK;  // this tick goes the ordinary way (first launches set up function attributes: not inside a capture); the next one builds the graph
   }
@@ -1435,7 +1526,7 @@ int mrsb_get_input_mode(mrsb_handle h, int64_t n, const int32_t* idx, int32_t* m
   if (n == 0) return MRSB_OK;
   rc = ensure_stage(h, sizeof(int32_t) * size_t(n));
   if (rc) return rc;
-  h->n_launches += launch_gather_u8(h->ds.mode, n, d_idx, reinterpret_cast<int32_t*>(h->d_stage), h->stream);
+  h->n_launches += launch_gather_u8(h->ds.mode, n, d_idx, reinterpret_cast<int32_t*>(h->d_stage), h->ds.perm, h->stream);
   CU(cudaMemcpyAsync(mode, h->d_stage, sizeof(int32_t) * size_t(n), cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   return MRSB_OK;
@@ -1449,7 +1540,7 @@ static int get_flags(mrsb_sim* h, int64_t n, const int32_t* idx, std::vector<uin
   if (n == 0) return MRSB_OK;
   rc = ensure_stage(h, sizeof(uint32_t) * size_t(n));
   if (rc) return rc;
-  h->n_launches += launch_gather_u32(h->ds.flags, n, d_idx, reinterpret_cast<uint32_t*>(h->d_stage), h->stream);
+  h->n_launches += launch_gather_u32(h->ds.flags, n, d_idx, reinterpret_cast<uint32_t*>(h->d_stage), h->ds.perm, h->stream);
   CU(cudaMemcpyAsync(out.data(), h->d_stage, sizeof(uint32_t) * size_t(n), cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   return MRSB_OK;
@@ -1559,7 +1650,7 @@ int mrsb_set_params(mrsb_handle h, int64_t n, const int32_t* idx, const mrsb_mod
   const int32_t* d_idx = nullptr;
   rc                   = stage_idx(h, n, idx, &d_idx);
   if (rc) return rc;
-  h->n_launches += launch_reset_pid(h->ds, n, d_idx, 0, PID_ROWS, h->stream);
+  h->n_launches += launch_reset_pid(h->ds, n, d_idx, 0, 12, h->stream);
   h->n_launches += launch_flag_update(h->ds, n, d_idx, ~FLAG_TAKEOFF, params->takeoff_patch_enabled ? FLAG_TAKEOFF : 0u, h->stream);
   return MRSB_OK;
 }
@@ -1584,27 +1675,27 @@ int mrsb_set_mixer_params(mrsb_handle h, int64_t n, const int32_t* idx, int32_t 
 int mrsb_set_rate_controller_params(mrsb_handle h, int64_t n, const int32_t* idx, double kp, double kd, double ki) {
   GUARD(h);
   const double v[3] = {kp, kd, ki};
-  return set_ctrl(h, n, idx, 18, 6, [](ParamSet& s, const double* v) { s.cp.rate_kp = v[0], s.cp.rate_kd = v[1], s.cp.rate_ki = v[2]; }, v);
+  return set_ctrl(h, n, idx, 9, 3, [](ParamSet& s, const double* v) { s.cp.rate_kp = v[0], s.cp.rate_kd = v[1], s.cp.rate_ki = v[2]; }, v);
 }
 int mrsb_set_attitude_controller_params(mrsb_handle h, int64_t n, const int32_t* idx, double kp, double kd, double ki, double max_rate_roll_pitch,
                                         double max_rate_yaw) {
   GUARD(h);
   const double v[5] = {kp, kd, ki, max_rate_roll_pitch, max_rate_yaw};
-  return set_ctrl(h, n, idx, 12, 6, [](ParamSet& s, const double* v) {
+  return set_ctrl(h, n, idx, 6, 3, [](ParamSet& s, const double* v) {
     s.cp.att_kp = v[0], s.cp.att_kd = v[1], s.cp.att_ki = v[2], s.cp.att_max_rate_roll_pitch = v[3], s.cp.att_max_rate_yaw = v[4];
   }, v);
 }
 int mrsb_set_velocity_controller_params(mrsb_handle h, int64_t n, const int32_t* idx, double kp, double kd, double ki, double max_acceleration) {
   GUARD(h);
   const double v[4] = {kp, kd, ki, max_acceleration};
-  return set_ctrl(h, n, idx, 6, 6, [](ParamSet& s, const double* v) {
+  return set_ctrl(h, n, idx, 3, 3, [](ParamSet& s, const double* v) {
     s.cp.vel_kp = v[0], s.cp.vel_kd = v[1], s.cp.vel_ki = v[2], s.cp.vel_max_acceleration = v[3];
   }, v);
 }
 int mrsb_set_position_controller_params(mrsb_handle h, int64_t n, const int32_t* idx, double kp, double kd, double ki, double max_velocity) {
   GUARD(h);
   const double v[4] = {kp, kd, ki, max_velocity};
-  return set_ctrl(h, n, idx, 0, 6, [](ParamSet& s, const double* v) {
+  return set_ctrl(h, n, idx, 0, 3, [](ParamSet& s, const double* v) {
     s.cp.pos_kp = v[0], s.cp.pos_kd = v[1], s.cp.pos_ki = v[2], s.cp.pos_max_velocity = v[3];
   }, v);
 }
@@ -1682,7 +1773,7 @@ static int edit_params_each(mrsb_sim* h, int64_t n, const int32_t* idx, const do
   const int32_t* d_idx = nullptr;
   rc                   = stage_idx(h, n, idx, &d_idx);
   if (rc) return rc;
-  h->n_launches += launch_reset_pid(h->ds, n, d_idx, 0, PID_ROWS, h->stream);
+  h->n_launches += launch_reset_pid(h->ds, n, d_idx, 0, 12, h->stream);
   CU(cudaGetLastError());
   return MRSB_OK;
 }
@@ -1938,6 +2029,7 @@ int mrsb_get_device_view(mrsb_handle h, mrsb_device_view* out) {
   out->ext_force   = h->ds.fext;
   out->flags       = h->ds.flags;
   out->input_mode  = h->ds.mode;
+  out->slot_of_uav = h->ds.perm;
   return MRSB_OK;
 }
 

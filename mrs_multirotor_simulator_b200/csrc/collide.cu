@@ -541,11 +541,14 @@ DEV void process_pair(const DevState& s, const DevGrid& g, int crash_mode, doubl
 // SIM:356-358: forces replace external_force_ for the next tick (zero in crash mode, SIM:315-319)
 #define NL_LIVE 0x80000000u     // bit 31 of nl_count[]: the UAV's external force may be non-zero
 #define NL_CROWDED 0x40000000u  // bit 30: more than MRSB_NL_CAP candidates; nl_items[0][uav] = its record in the table
+// li: (external) local index; the force rows and the flags live in the UAV's slot of the tiled arrays (DevState::perm)
+DEV int64_t slot_of(const DevState& s, int64_t li) { return s.perm ? int64_t(s.perm[li]) : li; }
 DEV void store_result(const DevState& s, int64_t li, const PairAcc& acc) {
-  s.fext[tix(F3_ROWS, 0, li)] = acc.fx;
-  s.fext[tix(F3_ROWS, 1, li)] = acc.fy;
-  s.fext[tix(F3_ROWS, 2, li)] = acc.fz;
-  if (acc.crashed_me) s.flags[li] |= FLAG_CRASHED;
+  const int64_t sl = slot_of(s, li);
+  s.fext[tix(F3_ROWS, 0, sl)] = acc.fx;
+  s.fext[tix(F3_ROWS, 1, sl)] = acc.fy;
+  s.fext[tix(F3_ROWS, 2, sl)] = acc.fz;
+  if (acc.crashed_me) s.flags[sl] |= FLAG_CRASHED;
 }
 DEV bool nonzero(const PairAcc& acc) {
   return !(acc.fx == 0.0 && acc.fy == 0.0 && acc.fz == 0.0);  // NaN counts as non-zero
@@ -695,9 +698,10 @@ __global__ void __launch_bounds__(128) build_lists_kernel(DevState s, DevGrid g)
       if (cnt == 0u && (live || write_all)) {
         // nobody within the list radius: this UAV is not visited again until the next rebuild, so its force
         // (left from an earlier collision, or written from outside) is replaced by zero right here (SIM:356-358)
-        s.fext[tix(F3_ROWS, 0, li)] = 0.0;
-        s.fext[tix(F3_ROWS, 1, li)] = 0.0;
-        s.fext[tix(F3_ROWS, 2, li)] = 0.0;
+        const int64_t sl            = slot_of(s, li);
+        s.fext[tix(F3_ROWS, 0, sl)] = 0.0;
+        s.fext[tix(F3_ROWS, 1, sl)] = 0.0;
+        s.fext[tix(F3_ROWS, 2, sl)] = 0.0;
         live                        = 0u;
       }
       if (cnt > MRSB_NL_CAP) {
@@ -837,7 +841,7 @@ DEV void check_one(const DevState& s, const DevGrid& g, int crash_mode, double r
   }
   const bool nz = nonzero(acc);
   if (live || nz) store_result(s, li, acc);
-  else if (acc.crashed_me) s.flags[li] |= FLAG_CRASHED;
+  else if (acc.crashed_me) s.flags[slot_of(s, li)] |= FLAG_CRASHED;
   if (nz != bool(word & NL_LIVE)) g.nl_count[li] = (word & ~NL_LIVE) | (nz ? NL_LIVE : 0u);
 }
 

@@ -45,8 +45,8 @@ static __host__ __device__ __forceinline__ int64_t tix(int rows, int row, int64_
 #define FF_ACC_HDG 6       // 3 rows
 #define FF_ACC_HDG_RATE 9  // 3 rows + heading_rate
 #define FF_ROWS 13
-// PID state rows: 2*k = last_error, 2*k+1 = integral; k = 0..2 position xyz, 3..5 velocity xyz,
-// 6..8 attitude xyz, 9..11 rate xyz
+// PID state rows: PID k = 0..2 position xyz, 3..5 velocity xyz, 6..8 attitude xyz, 9..11 rate xyz keeps its last_error in row k
+// and its integral in row 12 + k (the integrals of a controller whose ki is zero can then be left out of a launch's traffic)
 #define PID_ROWS 24
 
 // One parameter set = one airframe + one set of controller gains, in the form the kernels want.
@@ -96,9 +96,16 @@ struct DevState {
   // sharded runs with peer access ("pull" exchange): peers read this shard's slice of gpos straight out of this GPU's memory
   // over NVLink.  So that a peer can tell which parts of the slice can matter to it, the step kernel also keeps one bounding
   // box per warp (32 consecutive UAVs): 6 order-preserving uint32 codes of floats rounded outwards, [group][lo xyz, hi xyz].
-  uint32_t* gbox;  // [ld / 32][6], nullptr = not tracked
+  uint32_t* gbox;  // [n_groups32][6], nullptr = not tracked
+  int64_t   n_groups32;  // (n + 31) / 32
   int32_t  n_ranks, rank;
   uint32_t opts;   // STEP_OPT_* bits
+  // Batches with several airframes are BUCKETED at create: the tiled arrays hold the UAVs sorted by airframe, every bucket padded
+  // to whole tiles, so that each 128-UAV tile is uniform and the specialised kernels apply.  perm[e] = slot of (external, local)
+  // index e; inv[slot] = e, or -1 for a padding slot.  nullptr: identity.  gpos, geom, pset and the neighbour lists stay in
+  // external order.
+  const int32_t* perm;
+  const int32_t* inv;
   // neighbour lists of the collision pass: the stepping kernel atomicMax-es the float bits of the
   // largest squared displacement |x_end - x_start|^2 of this launch here (nullptr = not tracked)
   uint32_t* disp_max;
@@ -199,17 +206,18 @@ int launch_publish_positions(const DevState& s, cudaStream_t stream);
 int launch_scatter_input(const DevState& s, int mode, int64_t n, const int32_t* idx_dev, const double* payload_dev, int stride, cudaStream_t stream);
 // payload[k][0..rows) <-> rows [row0, row0+rows) of a tiled array with `rows_total` components
 int launch_scatter_rows(double* dst, int rows_total, int row0, int rows, int64_t n, const int32_t* idx_dev, const double* payload_dev, int stride,
-                        cudaStream_t stream);
+                        const int32_t* perm, cudaStream_t stream);
 int launch_gather_rows(const double* src, int rows_total, int row0, int rows, int64_t n, const int32_t* idx_dev, double* out_dev, int stride,
-                       cudaStream_t stream);
+                       const int32_t* perm, cudaStream_t stream);
 int launch_flag_update(const DevState& s, int64_t n, const int32_t* idx_dev, uint32_t and_mask, uint32_t or_mask, cudaStream_t stream);
-int launch_gather_u32(const uint32_t* src, int64_t n, const int32_t* idx_dev, uint32_t* out_dev, cudaStream_t stream);
-int launch_gather_u8(const uint8_t* src, int64_t n, const int32_t* idx_dev, int32_t* out_dev, cudaStream_t stream);
+int launch_gather_u32(const uint32_t* src, int64_t n, const int32_t* idx_dev, uint32_t* out_dev, const int32_t* perm, cudaStream_t stream);
+int launch_gather_u8(const uint8_t* src, int64_t n, const int32_t* idx_dev, int32_t* out_dev, const int32_t* perm, cudaStream_t stream);
 int launch_set_mode(const DevState& s, int64_t n, const int32_t* idx_dev, int mode, cudaStream_t stream);
 int launch_set_state_pos(const DevState& s, int64_t n, const int32_t* idx_dev, const double* xyz_dev, const double* hdg_dev, cudaStream_t stream);
 int launch_stash_vprev(const DevState& s, int64_t n, const int32_t* idx_dev, cudaStream_t stream);
 int launch_gather_vprev(const DevState& s, int64_t n, const int32_t* idx_dev, double* out_dev, cudaStream_t stream);
-int launch_reset_pid(const DevState& s, int64_t n, const int32_t* idx_dev, int row0, int rows, cudaStream_t stream);
+// zero the state (last error and integral) of PIDs [pid0, pid0 + n_pids)
+int launch_reset_pid(const DevState& s, int64_t n, const int32_t* idx_dev, int pid0, int n_pids, cudaStream_t stream);
 int launch_timeout_input(const DevState& s, int64_t n, const int32_t* idx_dev, cudaStream_t stream);
 int launch_tracker_cmd(const DevState& s, int64_t n, const int32_t* idx_dev, const double* rows_dev, cudaStream_t stream);
 int launch_observe(const DevState& s, int what, int64_t n, const int32_t* idx_dev, double* out_dev, int stride, cudaStream_t stream);

@@ -6,7 +6,14 @@
 namespace {
 
 #define DEV __device__ __forceinline__
-DEV int64_t at(const int32_t* idx, int64_t k) { return idx ? int64_t(idx[k]) : k; }
+// k-th addressed UAV: its (external) local index ...
+DEV int64_t ext(const int32_t* idx, int64_t k) { return idx ? int64_t(idx[k]) : k; }
+// ... and the slot of the tiled arrays it lives in: the identity unless the batch was bucketed by airframe at create
+// (DevState::perm, api.cu) so that every 128-UAV tile holds one airframe
+DEV int64_t at(const int32_t* perm, const int32_t* idx, int64_t k) {
+  const int64_t e = ext(idx, k);
+  return perm ? int64_t(perm[e]) : e;
+}
 
 inline unsigned nblk(int64_t n, int t = 256) { return unsigned((n + t - 1) / t); }
 
@@ -16,8 +23,9 @@ inline unsigned nblk(int64_t n, int t = 256) { return unsigned((n + t - 1) / t);
 __global__ void scatter_input_kernel(DevState s, int mode, int64_t n, const int32_t* __restrict__ idx, const double* __restrict__ payload, int stride) {
   const int64_t k = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (k >= n) return;
-  const int64_t i = at(idx, k);
-  if (i < 0 || i >= s.n) return;
+  const int64_t e = ext(idx, k);
+  if (e < 0 || e >= s.n) return;
+  const int64_t i = s.perm ? int64_t(s.perm[e]) : e;
   const double* p    = payload + k * stride;
   const int     rows = mode == MRSB_ACTUATOR_CMD ? MRSB_NM : (mode == MRSB_ATTITUDE_CMD ? 10 : (mode == MRSB_TILT_HDG_RATE_CMD ? 5 : 4));
   for (int r = 0; r < rows; r++) s.cmd[tix(CMD_ROWS, r, i)] = r < stride ? p[r] : 0.0;
@@ -34,45 +42,48 @@ __global__ void scatter_input_kernel(DevState s, int mode, int64_t n, const int3
 __global__ void set_mode_kernel(DevState s, int64_t n, const int32_t* __restrict__ idx, int mode) {
   const int64_t k = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (k >= n) return;
-  const int64_t i = at(idx, k);
-  if (i < 0 || i >= s.n) return;
+  const int64_t e = ext(idx, k);
+  if (e < 0 || e >= s.n) return;
+  const int64_t i = s.perm ? int64_t(s.perm[e]) : e;
   s.mode[i] = uint8_t(mode);
 }
 
 // payload[k][0 .. rows) -> rows [row0, row0+rows) of UAV i
 __global__ void scatter_rows_kernel(double* __restrict__ dst, int rows_total, int row0, int rows, int64_t n, const int32_t* __restrict__ idx,
-                                    const double* __restrict__ payload, int stride) {
+                                    const double* __restrict__ payload, int stride, const int32_t* __restrict__ perm) {
   const int64_t k = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (k >= n) return;
-  const int64_t i = at(idx, k);
+  const int64_t i = at(perm, idx, k);
   for (int r = 0; r < rows; r++) dst[tix(rows_total, row0 + r, i)] = payload[k * stride + r];
 }
 
 __global__ void gather_rows_kernel(const double* __restrict__ src, int rows_total, int row0, int rows, int64_t n, const int32_t* __restrict__ idx,
-                                   double* __restrict__ out, int stride) {
+                                   double* __restrict__ out, int stride, const int32_t* __restrict__ perm) {
   const int64_t k = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (k >= n) return;
-  const int64_t i = at(idx, k);
+  const int64_t i = at(perm, idx, k);
   for (int r = 0; r < rows; r++) out[k * stride + r] = src[tix(rows_total, row0 + r, i)];
 }
 
 __global__ void flag_update_kernel(DevState s, int64_t n, const int32_t* __restrict__ idx, uint32_t and_mask, uint32_t or_mask) {
   const int64_t k = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (k >= n) return;
-  const int64_t i = at(idx, k);
+  const int64_t i = at(s.perm, idx, k);
   s.flags[i]      = (s.flags[i] & and_mask) | or_mask;
 }
 
-__global__ void gather_u32_kernel(const uint32_t* __restrict__ src, int64_t n, const int32_t* __restrict__ idx, uint32_t* __restrict__ out) {
+__global__ void gather_u32_kernel(const uint32_t* __restrict__ src, int64_t n, const int32_t* __restrict__ idx, uint32_t* __restrict__ out,
+                                  const int32_t* __restrict__ perm) {
   const int64_t k = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (k >= n) return;
-  out[k] = src[at(idx, k)];
+  out[k] = src[at(perm, idx, k)];
 }
 
-__global__ void gather_u8_kernel(const uint8_t* __restrict__ src, int64_t n, const int32_t* __restrict__ idx, int32_t* __restrict__ out) {
+__global__ void gather_u8_kernel(const uint8_t* __restrict__ src, int64_t n, const int32_t* __restrict__ idx, int32_t* __restrict__ out,
+                                 const int32_t* __restrict__ perm) {
   const int64_t k = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (k >= n) return;
-  out[k] = int32_t(src[at(idx, k)]);
+  out[k] = int32_t(src[at(perm, idx, k)]);
 }
 
 // MultirotorModel::setStatePos (MM:439-446): x, _initial_pos_, R = AngleAxis(-heading, z)
@@ -80,7 +91,8 @@ __global__ void set_state_pos_kernel(DevState s, int64_t n, const int32_t* __res
                                      const double* __restrict__ hdg) {
   const int64_t k = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (k >= n) return;
-  const int64_t i  = at(idx, k);
+  const int64_t e  = ext(idx, k);
+  const int64_t i  = s.perm ? int64_t(s.perm[e]) : e;
   const double  px = xyz ? xyz[3 * k] : 0.0, py = xyz ? xyz[3 * k + 1] : 0.0, pz = xyz ? xyz[3 * k + 2] : 0.0;
   double        sn, cs;
   sincos(hdg ? -hdg[k] : -0.0, &sn, &cs);
@@ -98,7 +110,7 @@ __global__ void set_state_pos_kernel(DevState s, int64_t n, const int32_t* __res
   s.st[tix(ST_ROWS, 12, i)] = 0.0;
   s.st[tix(ST_ROWS, 13, i)] = 0.0;
   s.st[tix(ST_ROWS, 14, i)] = (1.0 - cs) + cs;
-  double* gp        = s.gpos + 3 * (s.shard_begin + i);
+  double* gp        = s.gpos + 3 * (s.shard_begin + e);
   gp[0]             = px;
   gp[1]             = py;
   gp[2]             = pz;
@@ -108,7 +120,7 @@ __global__ void set_state_pos_kernel(DevState s, int64_t n, const int32_t* __res
 __global__ void stash_vprev_kernel(DevState s, int64_t n, const int32_t* __restrict__ idx) {
   const int64_t k = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (k >= n) return;
-  const int64_t i = at(idx, k);
+  const int64_t i = at(s.perm, idx, k);
   if (s.flags[i] & FLAG_VPREV) return;
   for (int r = 0; r < 3; r++) s.vprev[tix(VPREV_ROWS, r, i)] = s.st[tix(ST_ROWS, 3 + r, i)];
   s.flags[i] |= FLAG_VPREV;
@@ -117,23 +129,26 @@ __global__ void stash_vprev_kernel(DevState s, int64_t n, const int32_t* __restr
 __global__ void gather_vprev_kernel(DevState s, int64_t n, const int32_t* __restrict__ idx, double* __restrict__ out) {
   const int64_t k = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (k >= n) return;
-  const int64_t i  = at(idx, k);
+  const int64_t i  = at(s.perm, idx, k);
   const bool    ov = s.flags[i] & FLAG_VPREV;
   for (int r = 0; r < 3; r++) out[3 * k + r] = ov ? s.vprev[tix(VPREV_ROWS, r, i)] : s.st[tix(ST_ROWS, 3 + r, i)];
 }
 
-__global__ void reset_pid_kernel(DevState s, int64_t n, const int32_t* __restrict__ idx, int row0, int rows) {
+__global__ void reset_pid_kernel(DevState s, int64_t n, const int32_t* __restrict__ idx, int pid0, int n_pids) {
   const int64_t k = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (k >= n) return;
-  const int64_t i = at(idx, k);
-  for (int r = row0; r < row0 + rows; r++) s.pid[tix(PID_ROWS, r, i)] = 0.0;
+  const int64_t i = at(s.perm, idx, k);
+  for (int r = pid0; r < pid0 + n_pids; r++) {
+    s.pid[tix(PID_ROWS, r, i)]      = 0.0;  // last error
+    s.pid[tix(PID_ROWS, 12 + r, i)] = 0.0;  // integral
+  }
 }
 
 __global__ void set_pset_kernel(int32_t* __restrict__ pset, int64_t n, const int32_t* __restrict__ idx, int64_t offset,
                                 const int32_t* __restrict__ values) {
   const int64_t k = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (k >= n) return;
-  pset[offset + at(idx, k)] = values[k];
+  pset[offset + ext(idx, k)] = values[k];
 }
 
 // UavSystemRos::callbackTrackerCmd (ROSW:987-1022): one tracker command row -> the four sticky feed-forwards.
@@ -141,7 +156,7 @@ __global__ void set_pset_kernel(int32_t* __restrict__ pset, int64_t n, const int
 __global__ void tracker_cmd_kernel(DevState s, int64_t n, const int32_t* __restrict__ idx, const double* __restrict__ rows) {
   const int64_t k = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (k >= n) return;
-  const int64_t i  = at(idx, k);
+  const int64_t i  = at(s.perm, idx, k);
   const double* r  = rows + MRSB_TRACKER_CMD_STRIDE * k;
   const bool    uh = r[7] != 0.0, uv = r[8] != 0.0, ur = r[9] != 0.0, ua = r[10] != 0.0;
   const double  v[3] = {uh ? r[0] : 0.0, uh ? r[1] : 0.0, uv ? r[2] : 0.0};
@@ -161,7 +176,7 @@ __global__ void set_geom_kernel(double* __restrict__ geom, int64_t n, const int3
                                 const DevParams* __restrict__ params) {
   const int64_t k = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (k >= n) return;
-  const int64_t    j = offset + at(idx, k);
+  const int64_t    j = offset + ext(idx, k);
   const DevParams& P = params[pset[j]];
   geom[4 * j + 0]    = P.arm_length;
   geom[4 * j + 1]    = P.prop_radius;
@@ -173,7 +188,7 @@ __global__ void set_geom_kernel(double* __restrict__ geom, int64_t n, const int3
 __global__ void timeout_input_kernel(DevState s, int64_t n, const int32_t* __restrict__ idx) {
   const int64_t k = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (k >= n) return;
-  const int64_t i    = at(idx, k);
+  const int64_t i    = at(s.perm, idx, k);
   const int     mode = s.mode[i];
   s.flags[i] &= ~FLAG_HAD_INPUT;  // time_last_input_ = 0 (ROSW:256-259): with iterate_without_input off the UAV stops until the next command
   auto          C    = [&](int row) -> double& { return s.cmd[tix(CMD_ROWS, row, i)]; };
@@ -240,7 +255,8 @@ DEV void quaternion_of(const double* m /* column-major */, double* q) {
 __global__ void observe_kernel(DevState s, int what, int64_t n, const int32_t* __restrict__ idx, double* __restrict__ out, int stride) {
   const int64_t k = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (k >= n) return;
-  const int64_t i = at(idx, k);
+  const int64_t e = ext(idx, k);
+  const int64_t i = s.perm ? int64_t(s.perm[e]) : e;
   double        x[3], v[3], R[9], w[3], q[4];
   for (int r = 0; r < 3; r++) {
     x[r] = s.st[tix(ST_ROWS, r, i)];
@@ -254,7 +270,7 @@ __global__ void observe_kernel(DevState s, int what, int64_t n, const int32_t* _
   if (what == 2 || what == 3) {
     const double bz   = R[8];
     const double tilt = acos((-R[6]) * 0.0 + ((-R[7]) * 0.0 + (-bz) * -1.0));
-    range             = bz > 0.0 ? (x[2] - s.params[s.pset[s.shard_begin + i]].ground_z) / cos(tilt) + 0.01 : 1.7976931348623157e308;
+    range             = bz > 0.0 ? (x[2] - s.params[s.pset[s.shard_begin + e]].ground_z) / cos(tilt) + 0.01 : 1.7976931348623157e308;
     if (range > 40.0) range = 41.0;
   }
   if (what == 0 || what == 3) {
@@ -303,14 +319,15 @@ int launch_set_mode(const DevState& s, int64_t n, const int32_t* idx, int mode, 
   return 1;
 }
 int launch_scatter_rows(double* dst, int rows_total, int row0, int rows, int64_t n, const int32_t* idx, const double* payload, int stride,
-                        cudaStream_t st) {
+                        const int32_t* perm, cudaStream_t st) {
   if (n <= 0) return 0;
-  scatter_rows_kernel<<<nblk(n), 256, 0, st>>>(dst, rows_total, row0, rows, n, idx, payload, stride);
+  scatter_rows_kernel<<<nblk(n), 256, 0, st>>>(dst, rows_total, row0, rows, n, idx, payload, stride, perm);
   return 1;
 }
-int launch_gather_rows(const double* src, int rows_total, int row0, int rows, int64_t n, const int32_t* idx, double* out, int stride, cudaStream_t st) {
+int launch_gather_rows(const double* src, int rows_total, int row0, int rows, int64_t n, const int32_t* idx, double* out, int stride, const int32_t* perm,
+                       cudaStream_t st) {
   if (n <= 0) return 0;
-  gather_rows_kernel<<<nblk(n), 256, 0, st>>>(src, rows_total, row0, rows, n, idx, out, stride);
+  gather_rows_kernel<<<nblk(n), 256, 0, st>>>(src, rows_total, row0, rows, n, idx, out, stride, perm);
   return 1;
 }
 int launch_flag_update(const DevState& s, int64_t n, const int32_t* idx, uint32_t and_mask, uint32_t or_mask, cudaStream_t st) {
@@ -318,14 +335,14 @@ int launch_flag_update(const DevState& s, int64_t n, const int32_t* idx, uint32_
   flag_update_kernel<<<nblk(n), 256, 0, st>>>(s, n, idx, and_mask, or_mask);
   return 1;
 }
-int launch_gather_u32(const uint32_t* src, int64_t n, const int32_t* idx, uint32_t* out, cudaStream_t st) {
+int launch_gather_u32(const uint32_t* src, int64_t n, const int32_t* idx, uint32_t* out, const int32_t* perm, cudaStream_t st) {
   if (n <= 0) return 0;
-  gather_u32_kernel<<<nblk(n), 256, 0, st>>>(src, n, idx, out);
+  gather_u32_kernel<<<nblk(n), 256, 0, st>>>(src, n, idx, out, perm);
   return 1;
 }
-int launch_gather_u8(const uint8_t* src, int64_t n, const int32_t* idx, int32_t* out, cudaStream_t st) {
+int launch_gather_u8(const uint8_t* src, int64_t n, const int32_t* idx, int32_t* out, const int32_t* perm, cudaStream_t st) {
   if (n <= 0) return 0;
-  gather_u8_kernel<<<nblk(n), 256, 0, st>>>(src, n, idx, out);
+  gather_u8_kernel<<<nblk(n), 256, 0, st>>>(src, n, idx, out, perm);
   return 1;
 }
 int launch_set_state_pos(const DevState& s, int64_t n, const int32_t* idx, const double* xyz, const double* hdg, cudaStream_t st) {
@@ -343,9 +360,9 @@ int launch_gather_vprev(const DevState& s, int64_t n, const int32_t* idx, double
   gather_vprev_kernel<<<nblk(n), 256, 0, st>>>(s, n, idx, out);
   return 1;
 }
-int launch_reset_pid(const DevState& s, int64_t n, const int32_t* idx, int row0, int rows, cudaStream_t st) {
+int launch_reset_pid(const DevState& s, int64_t n, const int32_t* idx, int pid0, int n_pids, cudaStream_t st) {
   if (n <= 0) return 0;
-  reset_pid_kernel<<<nblk(n), 256, 0, st>>>(s, n, idx, row0, rows);
+  reset_pid_kernel<<<nblk(n), 256, 0, st>>>(s, n, idx, pid0, n_pids);
   return 1;
 }
 int launch_tracker_cmd(const DevState& s, int64_t n, const int32_t* idx, const double* rows, cudaStream_t st) {

@@ -39,13 +39,14 @@ __device__ __forceinline__ uint32_t fenc(float f) {
 
 // positions of the state -> packed buffer (after set_state / a parity flip), plus the per-warp bounding boxes the peers filter by
 __global__ void __launch_bounds__(256) publish_positions_kernel(DevState s) {
-  const int64_t i      = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;  // blockDim is a multiple of 32: warps coincide with the 32-UAV groups
+  const int64_t i      = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;  // external index; blockDim is a multiple of 32: warps coincide with the 32-UAV groups
   const bool    inside = i < s.n;
   double        x = 0.0, y = 0.0, z = 0.0;
   if (inside) {
-    x          = s.st[tix(ST_ROWS, 0, i)];
-    y          = s.st[tix(ST_ROWS, 1, i)];
-    z          = s.st[tix(ST_ROWS, 2, i)];
+    const int64_t slot = s.perm ? int64_t(s.perm[i]) : i;
+    x          = s.st[tix(ST_ROWS, 0, slot)];
+    y          = s.st[tix(ST_ROWS, 1, slot)];
+    z          = s.st[tix(ST_ROWS, 2, slot)];
     double* gp = s.gpos + 3 * (s.shard_begin + i);
     gp[0]      = x;
     gp[1]      = y;
@@ -62,7 +63,7 @@ __global__ void __launch_bounds__(256) publish_positions_kernel(DevState s) {
     hi0 = __reduce_max_sync(full, hi0);
     hi1 = __reduce_max_sync(full, hi1);
     hi2 = __reduce_max_sync(full, hi2);
-    if ((threadIdx.x & 31) == 0 && i < s.ld) {
+    if ((threadIdx.x & 31) == 0 && i < s.n_groups32 * 32) {
       uint32_t* row = s.gbox + 6 * (i >> 5);
       row[0] = lo0, row[1] = lo1, row[2] = lo2, row[3] = hi0, row[4] = hi1, row[5] = hi2;
     }
@@ -84,6 +85,6 @@ int launch_prep_params(DevParams* params, int n_sets, double dt, cudaStream_t st
 
 int launch_publish_positions(const DevState& s, cudaStream_t stream) {
   if (s.n <= 0) return 0;
-  publish_positions_kernel<<<unsigned((s.ld + 255) / 256), 256, 0, stream>>>(s);
+  publish_positions_kernel<<<unsigned((s.n + 255) / 256), 256, 0, stream>>>(s);
   return 1;
 }

@@ -425,15 +425,17 @@ DEV void step_uav(const DevState& s, const TileIn& in, const int64_t tile, const
   const bool on_att  = live && mode0 >= MRSB_ATTITUDE_CMD;
   const bool on_rate = live && mode0 >= MRSB_ATTITUDE_RATE_CMD;
 
-  double pd[PID_ROWS];
+  // PID state of PID k (0-2 position, 3-5 velocity, 6-8 attitude, 9-11 rate): last error in row k, integral in row 12 + k.
+  // A rate PID whose ki is zero (the default, CTL/rate_controller.hpp:62-64: gains (4, .04, 0) * J_ii) never reads its integral, and
+  // every way of changing ki (setParams, setRateControllerParams) resets it: the three rows are dead and neither loaded nor stored.
+  const bool rate_int = P->rate_ki[0] != 0.0 || P->rate_ki[1] != 0.0 || P->rate_ki[2] != 0.0;
+  double     pe[12], pi[12];
 #pragma unroll
-  for (int r = 0; r < 6; r++) pd[r] = on_pos ? LD(t_pid, r) : 0.0;
-#pragma unroll
-  for (int r = 6; r < 12; r++) pd[r] = on_vel ? LD(t_pid, r) : 0.0;
-#pragma unroll
-  for (int r = 12; r < 18; r++) pd[r] = on_att ? LD(t_pid, r) : 0.0;
-#pragma unroll
-  for (int r = 18; r < 24; r++) pd[r] = on_rate ? LD(t_pid, r) : 0.0;
+  for (int k = 0; k < 12; k++) {
+    const bool on = k < 3 ? on_pos : (k < 6 ? on_vel : (k < 9 ? on_att : on_rate));
+    pe[k]         = on ? LD(t_pid, k) : 0.0;
+    pi[k]         = (on && (k < 9 || rate_int)) ? LD(t_pid, 12 + k) : 0.0;
+  }
 
   // command payload
   double c[CMD_ROWS];
@@ -513,18 +515,18 @@ DEV void step_uav(const DevState& s, const TileIn& in, const int64_t tile, const
       if (mode == MRSB_POSITION_CMD) {  // CTL/position_controller.hpp:73-86
         const Vec3   e   = vec - x;
         const double sat = P->pos_sat;
-        vec.x = pid(e.x, dt, inv_dt, P->pos_kp, P->pos_kd, P->pos_ki, sat, 1.0, pd[0], pd[1]);
-        vec.y = pid(e.y, dt, inv_dt, P->pos_kp, P->pos_kd, P->pos_ki, sat, 1.0, pd[2], pd[3]);
-        vec.z = pid(e.z, dt, inv_dt, P->pos_kp, P->pos_kd, P->pos_ki, sat, 1.0, pd[4], pd[5]);
+        vec.x = pid(e.x, dt, inv_dt, P->pos_kp, P->pos_kd, P->pos_ki, sat, 1.0, pe[0], pi[0]);
+        vec.y = pid(e.y, dt, inv_dt, P->pos_kp, P->pos_kd, P->pos_ki, sat, 1.0, pe[1], pi[1]);
+        vec.z = pid(e.z, dt, inv_dt, P->pos_kp, P->pos_kd, P->pos_ki, sat, 1.0, pe[2], pi[2]);
         vec   = vec + ff_vel;
         mode  = MRSB_VELOCITY_HDG_CMD;
       }
       if (mode == MRSB_VELOCITY_HDG_CMD || mode == MRSB_VELOCITY_HDG_RATE_CMD) {  // CTL/velocity_controller.hpp:68-102
         const Vec3   e   = vec - v;
         const double sat = P->vel_sat;
-        vec.x = pid(e.x, dt, inv_dt, P->vel_kp, P->vel_kd, P->vel_ki, sat, 1.0, pd[6], pd[7]);
-        vec.y = pid(e.y, dt, inv_dt, P->vel_kp, P->vel_kd, P->vel_ki, sat, 1.0, pd[8], pd[9]);
-        vec.z = pid(e.z, dt, inv_dt, P->vel_kp, P->vel_kd, P->vel_ki, sat, 1.0, pd[10], pd[11]);
+        vec.x = pid(e.x, dt, inv_dt, P->vel_kp, P->vel_kd, P->vel_ki, sat, 1.0, pe[3], pi[3]);
+        vec.y = pid(e.y, dt, inv_dt, P->vel_kp, P->vel_kd, P->vel_ki, sat, 1.0, pe[4], pi[4]);
+        vec.z = pid(e.z, dt, inv_dt, P->vel_kp, P->vel_kd, P->vel_ki, sat, 1.0, pe[5], pi[5]);
         vec   = vec + ff_acc;
         sc += ff_hdg_rate;
         mode = (mode == MRSB_VELOCITY_HDG_CMD) ? MRSB_ACCELERATION_HDG_CMD : MRSB_ACCELERATION_HDG_RATE_CMD;
@@ -566,9 +568,9 @@ DEV void step_uav(const DevState& s, const TileIn& in, const int64_t tile, const
           Rd.c0 = normalized(cross(Rd.c1, Rd.c2));
         }
         const Vec3 e = attitude_error(Rd, R);
-        double rx = pid(e.x, dt, inv_dt, P->att_kp, P->att_kd, P->att_ki, P->att_sat_rp, 0.1, pd[12], pd[13]);
-        double ry = pid(e.y, dt, inv_dt, P->att_kp, P->att_kd, P->att_ki, P->att_sat_rp, 0.1, pd[14], pd[15]);
-        double rz = pid(e.z, dt, inv_dt, P->att_kp, P->att_kd, P->att_ki, P->att_sat_yaw, 0.1, pd[16], pd[17]);
+        double rx = pid(e.x, dt, inv_dt, P->att_kp, P->att_kd, P->att_ki, P->att_sat_rp, 0.1, pe[6], pi[6]);
+        double ry = pid(e.y, dt, inv_dt, P->att_kp, P->att_kd, P->att_ki, P->att_sat_rp, 0.1, pe[7], pi[7]);
+        double rz = pid(e.z, dt, inv_dt, P->att_kp, P->att_kd, P->att_ki, P->att_sat_yaw, 0.1, pe[8], pi[8]);
         if (tilt) {
           // intrinsicBodyRateToHeadingRate (:177-206): d/dt atan2(R10, R00) under body rates (rx,ry,rz)
           const double rd00 = fma(R.c1.x, rz, -(R.c2.x * ry));  // (R*[w]x)(0,0)
@@ -601,9 +603,9 @@ DEV void step_uav(const DevState& s, const TileIn& in, const int64_t tile, const
       }
       if (mode == MRSB_ATTITUDE_RATE_CMD) {  // CTL/rate_controller.hpp:67-81
         const Vec3 e = vec - w;
-        vec.x = pid(e.x, dt, inv_dt, P->rate_kp[0], P->rate_kd[0], P->rate_ki[0], -1.0, 1.0, pd[18], pd[19]);
-        vec.y = pid(e.y, dt, inv_dt, P->rate_kp[1], P->rate_kd[1], P->rate_ki[1], -1.0, 1.0, pd[20], pd[21]);
-        vec.z = pid(e.z, dt, inv_dt, P->rate_kp[2], P->rate_kd[2], P->rate_ki[2], -1.0, 1.0, pd[22], pd[23]);
+        vec.x = pid(e.x, dt, inv_dt, P->rate_kp[0], P->rate_kd[0], P->rate_ki[0], -1.0, 1.0, pe[9], pi[9]);
+        vec.y = pid(e.y, dt, inv_dt, P->rate_kp[1], P->rate_kd[1], P->rate_ki[1], -1.0, 1.0, pe[10], pi[10]);
+        vec.z = pid(e.z, dt, inv_dt, P->rate_kp[2], P->rate_kd[2], P->rate_ki[2], -1.0, 1.0, pe[11], pi[11]);
         mode  = MRSB_CONTROL_GROUP_CMD;
       }
       if (mode == MRSB_CONTROL_GROUP_CMD) {  // CTL/mixer.hpp:107-144
@@ -652,21 +654,13 @@ DEV void step_uav(const DevState& s, const TileIn& in, const int64_t tile, const
 
     const bool last = ONE || (sub == k_sub - 1);
     if (last) {  // controller state is final for this launch: store it now, not after the RK4 (register pressure)
-      if (on_pos) {
 #pragma unroll
-        for (int r = 0; r < 6; r++) ST(o_pid, r, pd[r]);
-      }
-      if (on_vel) {
-#pragma unroll
-        for (int r = 6; r < 12; r++) ST(o_pid, r, pd[r]);
-      }
-      if (on_att) {
-#pragma unroll
-        for (int r = 12; r < 18; r++) ST(o_pid, r, pd[r]);
-      }
-      if (on_rate) {
-#pragma unroll
-        for (int r = 18; r < 24; r++) ST(o_pid, r, pd[r]);
+      for (int k = 0; k < 12; k++) {
+        const bool on = k < 3 ? on_pos : (k < 6 ? on_vel : (k < 9 ? on_att : on_rate));
+        if (on) {
+          ST(o_pid, k, pe[k]);
+          if (k < 9 || rate_int) ST(o_pid, 12 + k, pi[k]);
+        }
       }
     }
 
@@ -781,8 +775,8 @@ DEV void step_uav(const DevState& s, const TileIn& in, const int64_t tile, const
     if (new_flags != flags0) s.flags[i] = new_flags;
   }
   if (inside && (s.opts & STEP_OPT_GPOS)) {
-    // packed position for the collision pass / position download / the peers that pull it over NVLink
-    double* gp = s.gpos + 3 * (s.shard_begin + i);
+    // packed position for the collision pass / position download / the peers that pull it over NVLink (external index order)
+    double* gp = s.gpos + 3 * (s.shard_begin + (s.inv ? int64_t(s.inv[i]) : i));
     gp[0]      = x.x;
     gp[1]      = x.y;
     gp[2]      = x.z;
@@ -813,7 +807,8 @@ __global__ void __launch_bounds__(MRSB_STEP_THREADS, MRSB_STEP_MINB(ONE, MODE_T)
   in.fext = s.fext + (tile * F3_ROWS) * MRSB_TILE + threadIdx.x;
   const int64_t i = min(tile * MRSB_TILE + threadIdx.x, s.n - 1);
   uint32_t disp_bits = 0u;
-  step_uav<NM_T, MODE_T, ONE>(s, in, tile, s.flags[i], nullptr, s.pset[s.shard_begin + i], dt, inv_dt, k_sub, any_moment, disp_bits, [] {});
+  step_uav<NM_T, MODE_T, ONE>(s, in, tile, s.flags[i], nullptr, s.pset[s.shard_begin + (s.inv ? int64_t(s.inv[i]) : i)], dt, inv_dt, k_sub, any_moment, disp_bits,
+                              [] {});
   report_displacement(s, disp_bits);
 }
 
@@ -828,18 +823,21 @@ __global__ void __launch_bounds__(MRSB_STEP_THREADS, MRSB_STEP_MINB(ONE, MODE_T)
 #define SM_ROWS (SM_FEXT + F3_ROWS)
 
 template <int NM_T, int MODE_T>
-DEV void stage_tile(const DevState& s, double* sm, uint64_t* bar, int64_t tile) {
+DEV void stage_tile(const DevState& s, double* sm, uint64_t* bar, int64_t tile, bool rate_int) {
   static_assert(MODE_T >= 0 && NM_T > 0, "the staged kernel is for batches with a uniform input mode and motor count");
-  constexpr int      kRow      = MRSB_TILE * int(sizeof(double));
-  constexpr int      pid_lo    = MODE_T == MRSB_POSITION_CMD ? 0 : MODE_T >= MRSB_VELOCITY_HDG_RATE_CMD ? 6 : MODE_T >= MRSB_ATTITUDE_CMD ? 12 : MODE_T >= MRSB_ATTITUDE_RATE_CMD ? 18 : 24;
-  constexpr int      cmd_rows  = MODE_T == MRSB_ACTUATOR_CMD ? NM_T : MODE_T == MRSB_ATTITUDE_CMD ? 10 : MODE_T == MRSB_TILT_HDG_RATE_CMD ? 5 : 4;
-  constexpr bool     hdg       = MODE_T == MRSB_POSITION_CMD || MODE_T == MRSB_VELOCITY_HDG_CMD || MODE_T == MRSB_ACCELERATION_HDG_CMD;
-  constexpr uint32_t bytes     = uint32_t(kRow) * (ST_ROWS + NM_T + (PID_ROWS - pid_lo) + cmd_rows + (hdg ? 2 : 0) + F3_ROWS);
+  constexpr int  kRow     = MRSB_TILE * int(sizeof(double));
+  // first PID on the mode's path (PIDs 0-2 position, 3-5 velocity, 6-8 attitude, 9-11 rate; 12 = none)
+  constexpr int  pid_lo   = MODE_T == MRSB_POSITION_CMD ? 0 : MODE_T >= MRSB_VELOCITY_HDG_RATE_CMD ? 3 : MODE_T >= MRSB_ATTITUDE_CMD ? 6 : MODE_T >= MRSB_ATTITUDE_RATE_CMD ? 9 : 12;
+  constexpr int  cmd_rows = MODE_T == MRSB_ACTUATOR_CMD ? NM_T : MODE_T == MRSB_ATTITUDE_CMD ? 10 : MODE_T == MRSB_TILT_HDG_RATE_CMD ? 5 : 4;
+  constexpr bool hdg      = MODE_T == MRSB_POSITION_CMD || MODE_T == MRSB_VELOCITY_HDG_CMD || MODE_T == MRSB_ACCELERATION_HDG_CMD;
+  // integrals: rows 12 + pid_lo .. 23, without the three dead rate integrals when their ki is zero
+  const int      int_rows = pid_lo < 12 ? (rate_int ? 12 - pid_lo : 9 - pid_lo) : 0;
+  const uint32_t bytes    = uint32_t(kRow) * uint32_t(ST_ROWS + NM_T + (12 - pid_lo) + int_rows + cmd_rows + (hdg ? 2 : 0) + F3_ROWS);
   mbar_expect_tx(bar, bytes);
   tma_load(sm + SM_ST * MRSB_TILE, s.st + (tile * ST_ROWS) * MRSB_TILE, kRow * ST_ROWS, bar);
   tma_load(sm + SM_RPM * MRSB_TILE, s.rpm + (tile * MRSB_NM) * MRSB_TILE, kRow * NM_T, bar);
-  if (pid_lo < PID_ROWS)
-    tma_load(sm + (SM_PID + pid_lo) * MRSB_TILE, s.pid + (tile * PID_ROWS + pid_lo) * MRSB_TILE, kRow * (PID_ROWS - pid_lo), bar);
+  if (pid_lo < 12) tma_load(sm + (SM_PID + pid_lo) * MRSB_TILE, s.pid + (tile * PID_ROWS + pid_lo) * MRSB_TILE, kRow * (12 - pid_lo), bar);
+  if (int_rows > 0) tma_load(sm + (SM_PID + 12 + pid_lo) * MRSB_TILE, s.pid + (tile * PID_ROWS + 12 + pid_lo) * MRSB_TILE, uint32_t(kRow) * uint32_t(int_rows), bar);
   tma_load(sm + SM_CMD * MRSB_TILE, s.cmd + (tile * CMD_ROWS) * MRSB_TILE, kRow * cmd_rows, bar);
   if (hdg) tma_load(sm + (SM_CMD + CMD_COS) * MRSB_TILE, s.cmd + (tile * CMD_ROWS + CMD_COS) * MRSB_TILE, kRow * 2, bar);
   tma_load(sm + SM_FEXT * MRSB_TILE, s.fext + (tile * F3_ROWS) * MRSB_TILE, kRow * F3_ROWS, bar);
@@ -854,8 +852,9 @@ __global__ void __launch_bounds__(MRSB_STEP_THREADS, MRSB_STEP_MINB(ONE, MODE_T)
   __shared__ uint64_t bar;
   if (threadIdx.x == 0) mbar_init(&bar, 1);
   __syncthreads();
-  int64_t tile = blockIdx.x;
-  if (threadIdx.x == 0 && tile < n_tiles) stage_tile<NM_T, MODE_T>(s, sm, &bar, tile);
+  int64_t    tile     = blockIdx.x;
+  const bool rate_int = params.rate_ki[0] != 0.0 || params.rate_ki[1] != 0.0 || params.rate_ki[2] != 0.0;  // same test as step_uav
+  if (threadIdx.x == 0 && tile < n_tiles) stage_tile<NM_T, MODE_T>(s, sm, &bar, tile, rate_int);
   TileIn in;
   in.st   = sm + SM_ST * MRSB_TILE + threadIdx.x;
   in.rpm  = sm + SM_RPM * MRSB_TILE + threadIdx.x;
@@ -875,7 +874,7 @@ __global__ void __launch_bounds__(MRSB_STEP_THREADS, MRSB_STEP_MINB(ONE, MODE_T)
     phase ^= 1u;
     step_uav<NM_T, MODE_T, ONE>(s, in, tile, flags_cur, &params, 0, dt, inv_dt, k_sub, any_moment, disp_bits, [&] {
       __syncthreads();  // every lane has its inputs in registers: the image may be overwritten
-      if (threadIdx.x == 0 && next < n_tiles) stage_tile<NM_T, MODE_T>(s, sm, &bar, next);
+      if (threadIdx.x == 0 && next < n_tiles) stage_tile<NM_T, MODE_T>(s, sm, &bar, next, rate_int);
     });
     flags_cur = flags_next;
   }

@@ -179,3 +179,27 @@ def test_staged_equals_direct_bit_for_bit(frame, nm, mode, k):
     for key in direct:
         assert np.array_equal(direct[key], staged[key], equal_nan=True), f"{key} differs between the staged and the direct kernel"
     assert np.all(np.isfinite(staged["x"]))
+
+
+def test_c5_interleaved_airframes_run_the_staged_kernels_per_bucket():
+    """BASELINE config 5 as written: x500 / f550 / naki INTERLEAVED by index, ActuatorCmd re-drawn every 100 steps, ground on.
+    The library buckets the batch by airframe at create, so every airframe's UAVs run their uniform staged kernel
+    (<4|6|8, ACTUATOR, K=1>; 3 x 58,001 UAVs) — against the oracle (which knows nothing of buckets), 5 s."""
+    n = 3 * 58001
+    types = [af("x500", ground_enabled=True), af("f550", ground_enabled=True), af("naki", ground_enabled=True)]
+    tou = (np.arange(n) % 3).astype(np.int32)
+    orc, gpu = make_pair(types, tou, big_grid(n, 0.0))
+    for block in range(5):
+        cmd = commands(O.ACTUATOR_CMD, n, seed=200 + block)
+        orc.set_input(O.ACTUATOR_CMD, cmd)
+        gpu.set_input(O.ACTUATOR_CMD, cmd)
+        orc.make_step(0.01, 100, n_threads=THREADS)
+        for _ in range(100):
+            gpu.make_step(0.01)
+    info = gpu.step_info()
+    assert info["variant"] == "staged" and info["mode"] == O.ACTUATOR_CMD and info["n_motors"] == 8, info  # the last bucket launched: naki
+    so, sg = orc.get_state(), gpu.get_full_state()
+    for k in ("x", "v", "omega"):
+        scale = 1.0 + np.max(np.abs(so[k]))
+        assert np.max(np.abs(so[k] - sg[k])) <= 1e-7 * scale, k
+    assert np.max(np.abs(so["motor_rpm"] - sg["motor_rpm"])) <= 1e-5

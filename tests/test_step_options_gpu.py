@@ -211,3 +211,64 @@ def test_raw_rotation_from_set_state_is_orthonormalised_in_every_stage():
     for _ in range(300):
         gpu.make_step(0.01)
     assert_parity(orc, gpu, what="3 s after a raw R")
+
+
+def _mixed_flight(bucketed, n, crash):
+    """A mixed x500 / f550 / naki swarm (interleaved) through most of the API, with or without the bucketing by airframe."""
+    import os
+
+    from mrs_multirotor_simulator_b200 import UavBatch
+
+    if bucketed:
+        os.environ.pop("MRSB_NO_BUCKETS", None)
+    else:
+        os.environ["MRSB_NO_BUCKETS"] = "1"
+    try:
+        types = [af("x500", ground_enabled=True, ground_z=0.0), af("f550", ground_enabled=True, ground_z=0.0), af("naki", ground_enabled=True, ground_z=0.0)]
+        tou = (np.arange(n) * 7 % 3).astype(np.int32)
+        spawn = grid_spawn(n, pitch=1.6, z=3.0) + np.stack([rand(14, 0, n, -0.2, 0.2), rand(14, 1, n, -0.2, 0.2), rand(14, 2, n, -0.4, 0.4)], axis=1)
+        b = UavBatch(types, type_of_uav=tou, spawn_xyz=spawn, spawn_heading=rand(14, 3, n, -3, 3), n=n)
+        assert (b.device_view().slot_of_uav is not None) == bucketed
+        b.set_collisions(True, crash, 100.0)
+        b.set_pair_capacity(16 * n)
+        b.set_input(O.VELOCITY_HDG_RATE_CMD, vel_cmd(n, seed=15))
+        some = np.arange(3, n, 11, dtype=np.int32)
+        b.set_input(O.POSITION_CMD, np.concatenate([spawn[some] + 2.0, rand(16, 0, len(some), -3, 3)[:, None]], axis=1), idx=some)
+        b.set_feedforward("velocity_hdg", np.tile([0.1, -0.1, 0.0, 0.0], (len(some), 1)), idx=some)
+        pairs = 0
+        for t in range(120):
+            b.make_step(0.01)
+            b.handle_collisions()
+            if t == 40:
+                b.set_mass(2.0 + (some % 4) * 0.3, idx=some)
+                b.apply_force(np.tile([0.5, 0.0, 0.2], (len(some), 1)), idx=some)
+                b.set_state(idx=some[:50], x=spawn[some[:50]] + np.array([0.3, 0.3, 1.0]))
+                b.crash(some[-5:])
+            if t == 80:
+                b.timeout_input(idx=some)
+                b.set_controller_params("velocity", [2.5, 0.06, 0.02, 4.0], idx=some)
+            pairs += len(b.get_collision_pairs())
+        out = b.get_full_state()
+        out["force"] = b.get_force()
+        out["crashed"] = b.has_crashed()
+        out["mode"] = b.get_input_mode()
+        out["odom"] = b.get_odometry()
+        out["range"] = b.get_rangefinder()
+        out["pairs_last"] = b.get_collision_pairs()
+        out["mass"] = np.array([b.get_params(int(i)).mass for i in some[:20]])
+        b.close()
+        return out, pairs
+    finally:
+        os.environ.pop("MRSB_NO_BUCKETS", None)
+
+
+@pytest.mark.parametrize("crash", [False, True])
+def test_bucketing_by_airframe_changes_no_bit(crash):
+    """Batches with several airframes are stored sorted by airframe (whole tiles per airframe) so that the specialised kernels
+    run; everything a caller can see — state, forces, crash flags, pair lists, observations, per-UAV parameters, addressed by the
+    caller's own indices — must equal the unbucketed library (MRSB_NO_BUCKETS=1) bit for bit."""
+    a, pa = _mixed_flight(True, 3000, crash)
+    b, pb = _mixed_flight(False, 3000, crash)
+    assert pa == pb and pa > 0
+    for k in a:
+        assert np.array_equal(a[k], b[k], equal_nan=True), k
