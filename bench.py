@@ -143,9 +143,10 @@ def measured_peaks():
 
 def workload_config(n_gpus):
     """Identical in both arms (the driver compares them)."""
-    working_set = (N_UAVS // n_gpus) * (STEP_BYTES_VELOCITY_QUAD // 2 + 200) + N_UAVS * 64 // n_gpus
-    l2 = ("L2 flushed between timed steps (256 MiB memset, outside the event pairs)" if working_set < 2 * L2_BYTES else
-          f"per-GPU working set {working_set / 1e6:.0f} MB > 126 MB L2: inputs larger than L2, no flush")
+    # bytes one tick touches per GPU: the stepping kernel's algorithmic traffic (each byte read once or written once) + the collision pass'
+    working_set = (N_UAVS // n_gpus) * (STEP_BYTES_VELOCITY_QUAD + IMU_BYTES + COLLIDE_BYTES_PER_UAV)
+    l2 = ("L2 flushed between timed steps (256 MiB memset, outside the event pairs)" if working_set < L2_BYTES else
+          f"per-GPU working set {working_set / 1e6:.0f} MB per tick > 126 MB L2: inputs larger than L2, no flush")
     return {"workload": "C4: 1,048,576 x500 UAVs, 1024x1024 grid 4 m pitch, VelocityHdgRate commands, dt=0.01, K=1, ground plane + mutual collisions "
                         "(rebounce 100) every tick", "n_uavs": N_UAVS, "dt": DT, "k_substeps": 1, "collisions": "enabled, crash=false, rebounce=100",
             "sharding": f"{n_gpus} contiguous index shards (strong scaling), cross-shard neighbours read from the owning GPU every tick" if n_gpus > 1 else "single shard",
@@ -349,7 +350,7 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    def timed_block(batch, stream, steps, run_fn=None, step_fn=None):
+    def timed_block(batch, stream, steps, run_fn=None, step_fn=None, flush=flush):
         """Exactly `steps` steps between a barrier + synchronize on both sides, timed with CUDA events on the handle's stream; returns
         ms (max over ranks).  Per-GPU working set above L2: ONE event pair around one call that issues all the steps (run_fn).
         Otherwise every step has its own pair and the L2 flush runs between the pairs."""
@@ -423,6 +424,14 @@ def run_b200(args):
         parts = [torch.zeros_like(t) for _ in range(world)]
         dist.all_gather(parts, t)
         cs = sum(int(p[0].item()) | (int(p[1].item()) << 63) for p in parts) & 0xFFFFFFFFFFFFFFFF
+
+    # shards that fit into L2: the same blocks again without the flush between ticks (what a running simulation sees: tick t + 1
+    # reads what tick t wrote), reported beside the headline
+    resident = None
+    if flush:
+        rb = [timed_block(batch, stream, args.steps, run_fn=run_ticks, flush=False) for _ in range(args.reps)]
+        resident = {"value": N_UAVS * args.steps / (float(np.median(rb)) * 1e-3), "ms_per_step": float(np.median(rb)) / args.steps, "blocks_ms": rb,
+                    "note": "no L2 flush between ticks, one mrsb_run call per block"}
 
     # ---- roofline of the dominant kernel (the stepping kernel), timed alone ---------------------
     n_roof = min(max(args.steps, 50), 200)
@@ -618,7 +627,7 @@ def run_b200(args):
             "regime": f"mixed: timed after {args.fast_forward} untimed ticks of flight; value = median of {args.reps} blocks of {args.steps} ticks, each one mrsb_run call",
             "regimes": {"mixed": {"value": value, "ms_per_step": tick_ms, "blocks_ms": blocks, "best_block_value": N_UAVS * args.steps / (min(blocks) * 1e-3),
                                   "rebuild_fraction": (info1["rebuilds"] - info0["rebuilds"]) / passes, "directed_pairs_last_tick": pairs_last},
-                        "fresh_grid": fresh},
+                        "fresh_grid": fresh, "l2_resident": resident},
             "state_checksum": {"x_u64_sum": f"{cs:016x}", "after_ticks": ticks_flown,
                                "note": "wrapping sum of the uint64 words of every UAV's position after the timed region: identical for every --gpus N"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(cmd_host.numel() * 8), "d2h_bytes_per_step": int(pos_host[0].numel() * 8),

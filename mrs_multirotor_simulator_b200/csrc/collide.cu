@@ -16,7 +16,7 @@
 //                 rank = atomicAdd(count[bucket], 1).  Cells adjacent in x land in adjacent buckets,
 //                 so one stencil row is ONE contiguous range of the grouped records.
 //   K2c  scan     begin = exclusive prefix sum of count: one single-pass kernel (decoupled look-back
-//                 over 2048-item tiles, tickets handed out in scheduling order).
+//                 over 4096-item tiles, tickets handed out in scheduling order).
 //   K2d  scatter  rec[begin[bucket] + rank] = {x, y, z, index}  (32-byte records: a candidate costs
 //                 exactly one DRAM sector).  This is a counting sort: no radix passes.
 //                 Bucket B mirrors bucket 0, so a row never straddles the end of the table.
@@ -341,11 +341,12 @@ __global__ void __launch_bounds__(64) refresh_halo_kernel(DevState s, DevGrid g,
   }
 }
 
-// Exclusive prefix sum of `in` in ONE pass: tiles of 2048 items, tile numbers taken from a ticket counter (so a tile only ever
+// Exclusive prefix sum of `in` in ONE pass: tiles of 4096 items, tile numbers taken from a ticket counter (so a tile only ever
 // waits for tiles that are already running), per-tile status word {2-bit flag | 32-bit value}: A = the tile's own sum, P = the
 // inclusive prefix up to and including the tile; a warp looks back over 32 predecessors at a time.  state[0] = ticket counter,
 // state[1 + t] = status of tile t, all zero before the launch.
-#define SCAN_TILE 2048
+#define SCAN_PER_THREAD 16
+#define SCAN_TILE (256 * SCAN_PER_THREAD)
 #define SCAN_FLAG_A (1ull << 32)
 #define SCAN_FLAG_P (2ull << 32)
 // HASWORK: the items are neighbour-list count words and the value summed is "has something to check" (0 / 1) — the exclusive sum
@@ -358,22 +359,25 @@ __global__ void __launch_bounds__(256) scan_kernel(const uint32_t* __restrict__ 
   if (threadIdx.x == 0) s_tile = uint32_t(atomicAdd(&state[0], 1ull));
   __syncthreads();
   const int64_t tile = s_tile;
-  const int64_t base = tile * SCAN_TILE + int64_t(threadIdx.x) * 8;
-  uint32_t      v[8];
-  if (base + 8 <= n) {
-    const uint4 a = reinterpret_cast<const uint4*>(in + base)[0], b = reinterpret_cast<const uint4*>(in + base)[1];
-    v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w, v[4] = b.x, v[5] = b.y, v[6] = b.z, v[7] = b.w;
+  const int64_t base = tile * SCAN_TILE + int64_t(threadIdx.x) * SCAN_PER_THREAD;
+  uint32_t      v[SCAN_PER_THREAD];
+  if (base + SCAN_PER_THREAD <= n) {
+#pragma unroll
+    for (int q = 0; q < SCAN_PER_THREAD / 4; q++) {
+      const uint4 a = reinterpret_cast<const uint4*>(in + base)[q];
+      v[4 * q] = a.x, v[4 * q + 1] = a.y, v[4 * q + 2] = a.z, v[4 * q + 3] = a.w;
+    }
   } else {
 #pragma unroll
-    for (int k = 0; k < 8; k++) v[k] = base + k < n ? in[base + k] : 0u;
+    for (int k = 0; k < SCAN_PER_THREAD; k++) v[k] = base + k < n ? in[base + k] : 0u;
   }
   if (HASWORK) {
 #pragma unroll
-    for (int k = 0; k < 8; k++) v[k] = (v[k] & 0x7FFFFFFFu) != 0u ? 1u : 0u;  // everything but the NL_LIVE bit: candidates or the crowded mark
+    for (int k = 0; k < SCAN_PER_THREAD; k++) v[k] = (v[k] & 0x7FFFFFFFu) != 0u ? 1u : 0u;  // everything but the NL_LIVE bit: candidates or the crowded mark
   }
   uint32_t mine = 0;
 #pragma unroll
-  for (int k = 0; k < 8; k++) mine += v[k];
+  for (int k = 0; k < SCAN_PER_THREAD; k++) mine += v[k];
   uint32_t incl = mine;  // inclusive scan of the thread sums inside the warp
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
@@ -417,21 +421,19 @@ __global__ void __launch_bounds__(256) scan_kernel(const uint32_t* __restrict__ 
   }
   __syncthreads();
   uint32_t run = s_prefix + warp_off + (incl - mine);
-  if (base + 8 <= n) {
-    uint4 a, b;
-    a.x = run, run += v[0];
-    a.y = run, run += v[1];
-    a.z = run, run += v[2];
-    a.w = run, run += v[3];
-    b.x = run, run += v[4];
-    b.y = run, run += v[5];
-    b.z = run, run += v[6];
-    b.w = run;
-    reinterpret_cast<uint4*>(out + base)[0] = a;
-    reinterpret_cast<uint4*>(out + base)[1] = b;
+  if (base + SCAN_PER_THREAD <= n) {
+#pragma unroll
+    for (int q = 0; q < SCAN_PER_THREAD / 4; q++) {
+      uint4 a;
+      a.x = run, run += v[4 * q];
+      a.y = run, run += v[4 * q + 1];
+      a.z = run, run += v[4 * q + 2];
+      a.w = run, run += v[4 * q + 3];
+      reinterpret_cast<uint4*>(out + base)[q] = a;
+    }
   } else {
 #pragma unroll
-    for (int k = 0; k < 8; k++) {
+    for (int k = 0; k < SCAN_PER_THREAD; k++) {
       if (base + k < n) out[base + k] = run;
       run += v[k];
     }
@@ -635,8 +637,8 @@ __global__ void __launch_bounds__(128, MRSB_COLLIDE_MINB) collide_kernel(DevStat
 
 // ---- neighbour lists ---------------------------------------------------------------------------
 
-// FOUR LANES PER RECORD, one per stencil row: lane k of a record walks the record range of row (cy0 + (k & 1), cz0 + (k >> 1)).
-// Every iteration each lane tests one candidate; the four lanes of a record learn from one ballot how many of them accept,
+// FOUR LANES PER RECORD: lane k of a record looks up the record range of stencil row (cy0 + (k & 1), cz0 + (k >> 1)); the four
+// ranges' candidates are then dealt to the four lanes round-robin.  Every round each lane tests two candidates; the four lanes of a record learn from one ballot how many of them accept,
 // which gives every accepted candidate its list slot without atomics.  A warp handles 8 records, a CTA 32; CTAs stride over the
 // table.  Afterwards lane 0 of the record writes the count word.
 __global__ void __launch_bounds__(128) build_lists_kernel(DevState s, DevGrid g) {
@@ -657,30 +659,42 @@ __global__ void __launch_bounds__(128) build_lists_kernel(DevState s, DevGrid g)
     const int64_t gi   = __double_as_longlong(q.w);
     const int64_t li   = gi - s.shard_begin;
     const bool    mine = has && li >= 0 && li < s.n;  // halo records are only candidates
-    uint32_t      lo = 0, hi = 0;
-    int           cy = 0, cz = 0;
+    // lane k looks up the record range of stencil row k = (cy0 + (k & 1), cz0 + (k >> 1)); the quad then shares the four ranges and
+    // deals their candidates out round-robin, so that every lane has the same amount of work whatever the rows' lengths are
+    // (rows of the cell layer above or below the swarm are empty)
+    const int cx0 = cell_of(q.x - g.reach, g.inv_cell), cy0 = cell_of(q.y - g.reach, g.inv_cell), cz0 = cell_of(q.z - g.reach, g.inv_cell);
+    uint32_t  lo = 0, len = 0;
     if (mine) {
-      cy                = cell_of(q.y - g.reach, g.inv_cell) + (k & 1);
-      cz                = cell_of(q.z - g.reach, g.inv_cell) + (k >> 1);
-      const uint32_t b0 = (row_hash(cy, cz) + uint32_t(cell_of(q.x - g.reach, g.inv_cell))) & mask;
+      const uint32_t b0 = (row_hash(cy0 + (k & 1), cz0 + (k >> 1)) + uint32_t(cx0)) & mask;
       lo                = g.begin[b0];
-      hi                = g.begin[b0 + 2];
+      len               = g.begin[b0 + 2] - lo;
     }
+    const int      qb  = lane & ~3;
+    const uint32_t lo0 = __shfl_sync(full, lo, qb), lo1 = __shfl_sync(full, lo, qb + 1), lo2 = __shfl_sync(full, lo, qb + 2), lo3 = __shfl_sync(full, lo, qb + 3);
+    const uint32_t c1  = __shfl_sync(full, len, qb);
+    const uint32_t c2  = c1 + __shfl_sync(full, len, qb + 1);
+    const uint32_t c3  = c2 + __shfl_sync(full, len, qb + 2);
+    const uint32_t tot = c3 + __shfl_sync(full, len, qb + 3);
+    auto where = [&](uint32_t c, int& row) -> uint32_t {  // candidate c of the concatenated ranges: its row and its record index
+      row = int(c >= c1) + int(c >= c2) + int(c >= c3);
+      return row == 0 ? lo0 + c : (row == 1 ? lo1 + (c - c1) : (row == 2 ? lo2 + (c - c2) : lo3 + (c - c3)));
+    };
     uint32_t cnt = 0;
-    // four candidates of the row at a time: the loads first (independent, all in flight together), then the tests
-    for (uint32_t t0 = lo; __any_sync(full, t0 < hi); t0 += 4) {
-      double4 r[4];
+    for (uint32_t c = uint32_t(k); __any_sync(full, c < tot); c += 8) {
+      // two candidates per lane and round: both loads first, then the tests
+      double4 r[2];
+      int     row[2] = {0, 0};
 #pragma unroll
-      for (int u = 0; u < 4; u++)
-        if (t0 + u < hi) r[u] = g.rec[t0 + u];
+      for (int u = 0; u < 2; u++)
+        if (c + 4 * u < tot) r[u] = g.rec[where(c + 4 * u, row[u])];
 #pragma unroll
-      for (int u = 0; u < 4; u++) {
+      for (int u = 0; u < 2; u++) {
         bool    take = false;
         int32_t gj   = 0;
-        if (t0 + u < hi) {
+        if (c + 4 * u < tot) {
           gj = int32_t(__double_as_longlong(r[u].w));
-          if (int64_t(gj) != gi && nf_dist2(q.x, q.y, q.z, r[u].x, r[u].y, r[u].z) < g.list_r2 && cell_of(r[u].y, g.inv_cell) == cy &&
-              cell_of(r[u].z, g.inv_cell) == cz)  // the last two: not a bucket alias, not seen in another row
+          if (int64_t(gj) != gi && nf_dist2(q.x, q.y, q.z, r[u].x, r[u].y, r[u].z) < g.list_r2 && cell_of(r[u].y, g.inv_cell) == cy0 + (row[u] & 1) &&
+              cell_of(r[u].z, g.inv_cell) == cz0 + (row[u] >> 1))  // the last two: not a bucket alias, not seen in another row
             take = true;
         }
         const uint32_t bal = __ballot_sync(full, take) & quad;

@@ -428,13 +428,13 @@ DEV void step_uav(const DevState& s, const TileIn& in, const int64_t tile, const
   // PID state of PID k (0-2 position, 3-5 velocity, 6-8 attitude, 9-11 rate): last error in row k, integral in row 12 + k.
   // A rate PID whose ki is zero (the default, CTL/rate_controller.hpp:62-64: gains (4, .04, 0) * J_ii) never reads its integral, and
   // every way of changing ki (setParams, setRateControllerParams) resets it: the three rows are dead and neither loaded nor stored.
-  const bool rate_int = P->rate_ki[0] != 0.0 || P->rate_ki[1] != 0.0 || P->rate_ki[2] != 0.0;
-  double     pe[12], pi[12];
+#define RATE_INT (P->rate_ki[0] != 0.0 || P->rate_ki[1] != 0.0 || P->rate_ki[2] != 0.0)
+  double pe[12], pi[12];
 #pragma unroll
   for (int k = 0; k < 12; k++) {
     const bool on = k < 3 ? on_pos : (k < 6 ? on_vel : (k < 9 ? on_att : on_rate));
     pe[k]         = on ? LD(t_pid, k) : 0.0;
-    pi[k]         = (on && (k < 9 || rate_int)) ? LD(t_pid, 12 + k) : 0.0;
+    pi[k]         = (on && (k < 9 || RATE_INT)) ? LD(t_pid, 12 + k) : 0.0;
   }
 
   // command payload
@@ -659,7 +659,7 @@ DEV void step_uav(const DevState& s, const TileIn& in, const int64_t tile, const
         const bool on = k < 3 ? on_pos : (k < 6 ? on_vel : (k < 9 ? on_att : on_rate));
         if (on) {
           ST(o_pid, k, pe[k]);
-          if (k < 9 || rate_int) ST(o_pid, 12 + k, pi[k]);
+          if (k < 9 || RATE_INT) ST(o_pid, 12 + k, pi[k]);
         }
       }
     }
@@ -784,6 +784,7 @@ DEV void step_uav(const DevState& s, const TileIn& in, const int64_t tile, const
   if (s.gbox) store_group_box(s.gbox + 6 * (tile * (MRSB_TILE / 32) + (threadIdx.x >> 5)), inside, x);
 #undef LD
 #undef ST
+#undef RATE_INT
 }
 
 // Largest squared displacement of the launch (float bits) -> DevState::disp_max: one atomic per warp
@@ -823,7 +824,8 @@ __global__ void __launch_bounds__(MRSB_STEP_THREADS, MRSB_STEP_MINB(ONE, MODE_T)
 #define SM_ROWS (SM_FEXT + F3_ROWS)
 
 template <int NM_T, int MODE_T>
-DEV void stage_tile(const DevState& s, double* sm, uint64_t* bar, int64_t tile, bool rate_int) {
+DEV void stage_tile(const DevState& s, const DevParams& P, double* sm, uint64_t* bar, int64_t tile) {
+  const bool rate_int = P.rate_ki[0] != 0.0 || P.rate_ki[1] != 0.0 || P.rate_ki[2] != 0.0;  // same test as step_uav
   static_assert(MODE_T >= 0 && NM_T > 0, "the staged kernel is for batches with a uniform input mode and motor count");
   constexpr int  kRow     = MRSB_TILE * int(sizeof(double));
   // first PID on the mode's path (PIDs 0-2 position, 3-5 velocity, 6-8 attitude, 9-11 rate; 12 = none)
@@ -852,9 +854,8 @@ __global__ void __launch_bounds__(MRSB_STEP_THREADS, MRSB_STEP_MINB(ONE, MODE_T)
   __shared__ uint64_t bar;
   if (threadIdx.x == 0) mbar_init(&bar, 1);
   __syncthreads();
-  int64_t    tile     = blockIdx.x;
-  const bool rate_int = params.rate_ki[0] != 0.0 || params.rate_ki[1] != 0.0 || params.rate_ki[2] != 0.0;  // same test as step_uav
-  if (threadIdx.x == 0 && tile < n_tiles) stage_tile<NM_T, MODE_T>(s, sm, &bar, tile, rate_int);
+  int64_t tile = blockIdx.x;
+  if (threadIdx.x == 0 && tile < n_tiles) stage_tile<NM_T, MODE_T>(s, params, sm, &bar, tile);
   TileIn in;
   in.st   = sm + SM_ST * MRSB_TILE + threadIdx.x;
   in.rpm  = sm + SM_RPM * MRSB_TILE + threadIdx.x;
@@ -874,7 +875,7 @@ __global__ void __launch_bounds__(MRSB_STEP_THREADS, MRSB_STEP_MINB(ONE, MODE_T)
     phase ^= 1u;
     step_uav<NM_T, MODE_T, ONE>(s, in, tile, flags_cur, &params, 0, dt, inv_dt, k_sub, any_moment, disp_bits, [&] {
       __syncthreads();  // every lane has its inputs in registers: the image may be overwritten
-      if (threadIdx.x == 0 && next < n_tiles) stage_tile<NM_T, MODE_T>(s, sm, &bar, next, rate_int);
+      if (threadIdx.x == 0 && next < n_tiles) stage_tile<NM_T, MODE_T>(s, params, sm, &bar, next);
     });
     flags_cur = flags_next;
   }

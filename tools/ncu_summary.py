@@ -59,5 +59,53 @@ def kernels(path):
                 print(f"  {w:70s} {r[i]:>16s} {U[i]}")
 
 
+def fp64(path, n_uavs=1048576, pattern="uav_step"):
+    """Executed instructions of the stepping kernel per UAV-step, summed by opcode from the source page (needs -lineinfo + --import-source on)."""
+    import json
+    import re
+
+    raw = subprocess.run(["ncu", "-i", path, "--page", "source", "--csv", "--kernel-name", f"regex:{pattern}"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    name = rows[0][1]
+    H = rows[1]
+    si, ti = H.index("Source"), H.index("Thread Instructions Executed")
+    per = collections.Counter()
+    seen_kernels = 0
+    for r in rows[2:]:
+        if r and r[0] == "Kernel Name":  # a second launch of the same kernel follows: one is enough
+            break
+        if len(r) <= ti:
+            continue
+        m = re.match(r"\s*(?:@!?U?P\d+\s+)?([A-Z0-9_]+)", r[si])
+        if not m:
+            continue
+        per[m.group(1).split(".")[0]] += float(r[ti])
+    tot = sum(per.values())
+    g = lambda k: per.get(k, 0.0) / n_uavs
+    out = {"kernel": name, "per_uav_step": {k: round(g(k), 1) for k in ("DFMA", "DMUL", "DADD", "DSETP", "MUFU")}, "source": f"ncu --set full --import-source on, per-instruction 'Thread Instructions Executed' of {path} summed by opcode (DFMA = 2 flop)"}
+    out["per_uav_step"]["all_instructions"] = round(tot / n_uavs, 1)
+    out["executed_fp64_flop_per_uav_step"] = round(2 * g("DFMA") + g("DMUL") + g("DADD"), 1)
+    out["as_written_census_flop_per_uav_step"] = 2550
+    print(json.dumps(out, indent=1))
+
+
+def traffic(path, n_uavs=1048576, pattern="uav_step"):
+    import json
+
+    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    H, U = rows[0], rows[1]
+    for r in rows[2:]:
+        if pattern in r[H.index("Kernel Name")]:
+            def val(metric):
+                i = H.index(metric)
+                v = float(r[i].replace(",", ""))
+                return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[U[i]]
+            rd, wr = val("dram__bytes_read.sum"), val("dram__bytes_write.sum")
+            print(json.dumps({"kernel": r[H.index("Kernel Name")], "n_uavs": n_uavs, "dram_bytes_read": rd, "dram_bytes_write": wr, "dram_bytes_per_launch": rd + wr,
+                              "dram_bytes_per_uav_step": round((rd + wr) / n_uavs, 2), "source": f"ncu --set full --clock-control none, {path}"}, indent=1))
+            return
+
+
 if __name__ == "__main__":
-    {"launches": launches, "kernels": kernels}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "kernels": kernels, "fp64": fp64, "traffic": traffic}[sys.argv[1]](sys.argv[2])
