@@ -155,6 +155,12 @@ public:
   void makeStep(double dt, int k_substeps = 1) { check(mrsb_make_step(h_, dt, k_substeps)); }
   void setCollisions(bool enabled, bool crash, double rebounce) { check(mrsb_set_collisions(h_, enabled, crash, rebounce)); }
   void handleCollisions() { check(mrsb_handle_collisions(h_)); }
+  // n_ticks of makeStep + handleCollisions without host synchronisation (one CUDA graph launch per tick)
+  void run(double dt, int n_ticks, int k_substeps = 1, bool with_collisions = true) { check(mrsb_run(h_, dt, k_substeps, n_ticks, with_collisions)); }
+  // UavSystemRos::_iterate_without_input_ (uav_system_ros.cpp:52, 265)
+  void setIterateWithoutInput(bool enabled) { check(mrsb_set_iterate_without_input(h_, enabled)); }
+  // optional per-step rows: the fabricated accelerometer (multirotor_model.hpp:280-281) and the packed positions
+  void setOutputs(bool imu, bool positions) { check(mrsb_set_outputs(h_, (imu ? MRSB_OUT_IMU : 0u) | (positions ? MRSB_OUT_POSITIONS : 0u))); }
   std::vector<std::array<int32_t, 2>> collisionPairs() {
     int64_t n = 0;
     check(mrsb_get_collision_pairs(h_, nullptr, 0, &n));

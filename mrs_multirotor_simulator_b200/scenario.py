@@ -108,6 +108,7 @@ class Scenario:
             b.make_step(0.01)
             b.make_step(0.01)
         b.set_collisions(self.collisions_enabled, self.collisions_crash, self.collisions_rebounce)
+        b.set_iterate_without_input(self.iterate_without_input)  # uav_system_ros.cpp:265
         return b
 
 
