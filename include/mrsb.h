@@ -331,8 +331,9 @@ int mrsb_get_timeline(mrsb_handle h, uint64_t* out, int64_t max_passes, int64_t*
 int mrsb_get_collision_info(mrsb_handle h, double* out8);
 
 /* ---- sharded operation (one handle per GPU / process) --------------------------------------
- * The cross-shard exchange is ONE all-gather per collision pass of the packed positions
- * (n_global*3 doubles).  Two ways to provide it:
+ * A shard's collision pass needs the positions of the remote UAVs near its own.  With peer access
+ * (mode 2 below) it fetches them itself; otherwise the exchange is ONE all-gather per collision
+ * pass of the packed positions (n_global*3 doubles), provided in one of two ways:
  *  (a) in-library NCCL: rank 0 calls mrsb_nccl_unique_id, the caller ships the 128 bytes to all
  *      ranks (MPI, torch.distributed, a file …), every rank calls mrsb_comm_init_nccl;
  *  (b) caller-run collective: mrsb_gather_buffer returns the device pointer of the n_global*3

@@ -370,7 +370,7 @@ class UavBatch:
         check(self._L.mrsb_comm_init_nccl(self.h, n_ranks, rank, buf))
 
     def exchange_mode(self):
-        """0 single shard, 1 NCCL all-gather per tick, 2 fused peer stores from the stepping kernel."""
+        """0 single shard, 1 NCCL all-gather per tick, 2 pull over peer memory (hand-shake + halo fetch over NVLink)."""
         return int(self._L.mrsb_exchange_mode(self.h))
 
     def gather_buffer(self):

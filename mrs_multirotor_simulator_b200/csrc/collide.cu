@@ -1,6 +1,6 @@
 // collide.cu — K2/K3: MultirotorSimulator::handleCollisions (SIM:295-359) as a uniform-grid spatial
-// hash over the packed positions of the swarm (after the cross-shard all-gather), queried for this
-// shard's UAVs only.
+// hash over the packed positions of this shard and of the halo of remote UAVs around it, queried for
+// this shard's UAVs only.
 //
 // The reference rebuilds a nanoflann KD-tree every tick and runs one radius query per UAV with
 // squared "radius" 3.0 (SIM:309-328).  Here, per pass:
@@ -49,8 +49,8 @@
 // forces a rebuild.  A UAV with more than NL_CAP candidates keeps no list: it remembers where its
 // record sits in the (now ageing) table and, every pass, walks the stencil of its build-time cell —
 // the records there are a superset of its possible neighbours for as long as the lists are valid —
-// testing each candidate's CURRENT position (`check_crowded`).  Only the crowded UAVs pay for that.  Sharded handles use the lists when the fused exchange
-// carries every rank's displacement bound (api.cu), the full pass otherwise.
+// testing each candidate's CURRENT position (`check_crowded`).  Only the crowded UAVs pay for that.  Sharded handles use the lists when the peer
+// hand-shake carries every rank's displacement bound (pull exchange, api.cu), the full pass otherwise.
 // The rebuild's list kernel works with FOUR LANES PER UAV, one per stencil row: each lane walks the
 // (short) record range of its row, the four lanes of a UAV agree on list slots through a ballot, and
 // the UAVs that have anything to check (a candidate, or the crowded mark) are appended to

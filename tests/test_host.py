@@ -119,3 +119,71 @@ def test_neighbour_list_validity_argument_on_a_numpy_model():
         assert not np.any(true & ~lists), tick  # every true neighbour is still listed
         hits += int(true.sum())
     assert 0 < rebuilds < 100 and hits > 0, (rebuilds, hits)
+
+
+def test_pull_exchange_buffer_protocol_on_a_scheduler_model():
+    """Host model of the pull exchange's hazard argument (api.cu `pass_no` / collide.cu `decide_kernel`): every rank owns
+    two position buffers; collision pass k READS buffer k & 1 of every peer after the hand-shake of pass k (it has sent its own
+    pass number and seen k from every peer), and everything a rank writes between its passes k - 1 and k goes to buffer k & 1.
+    Ranks are driven by a random scheduler (any interleaving a set of independent streams could produce, with any number of
+    writes between passes); the model checks that no buffer is ever written while a peer reads it, and that a reader always sees
+    the owner's latest complete positions of the pass it is in."""
+    rng = np.random.default_rng(7)
+    for trial in range(200):
+        G = int(rng.integers(2, 5))
+        n_pass = 6
+        # per-rank program: for each pass k = 1..n_pass: some writes (0..3, each bumps a version), then signal(k), wait, read, done
+        prog = []
+        for r in range(G):
+            ops = []
+            for k in range(1, n_pass + 1):
+                ops += [("write", k)] * int(rng.integers(0, 4)) + [("signal", k), ("wait", k), ("read_begin", k), ("read_end", k)]
+            prog.append(ops)
+        pc = [0] * G
+        flags = [[0] * G for _ in range(G)]      # flags[r][s]: last pass number rank s told rank r
+        buf = [[0, 0] for _ in range(G)]         # version stored in buffer b of rank r
+        version = [0] * G                        # latest position version of rank r (what `st` holds)
+        wrote = [False] * G                      # wrote_since_pass
+        reading = [[None] * G for _ in range(G)]  # reading[a][b] = buffer index rank a currently reads of rank b
+        at_signal = [dict() for _ in range(G)]    # version rank r held when it entered pass k
+        while any(pc[r] < len(prog[r]) for r in range(G)):
+            ready = []
+            for r in range(G):
+                if pc[r] >= len(prog[r]):
+                    continue
+                op, k = prog[r][pc[r]]
+                if op == "wait" and any(flags[r][s] < k for s in range(G) if s != r):
+                    continue  # blocked in the hand-shake
+                ready.append(r)
+            assert ready, "deadlock"
+            r = int(rng.choice(ready))
+            op, k = prog[r][pc[r]]
+            pc[r] += 1
+            w = k & 1  # buffer written before pass k and read during pass k
+            if op == "write":
+                assert all(reading[a][r] != w for a in range(G)), "a peer is reading the buffer being written"
+                version[r] += 1
+                buf[r][w] = version[r]
+                wrote[r] = True
+            elif op == "signal":
+                if not wrote[r]:  # nothing wrote positions since the last pass: publish_positions into the buffer of this pass
+                    assert all(reading[a][r] != w for a in range(G))
+                    buf[r][w] = version[r]
+                at_signal[r][k] = version[r]
+                for s in range(G):
+                    if s != r:
+                        flags[s][r] = k
+            elif op == "read_begin":
+                for s in range(G):
+                    if s != r:
+                        reading[r][s] = w
+                        # the owner has signalled pass k, so its buffer k & 1 holds the positions it had when it entered pass k;
+                        # it may have moved on since, but only into the OTHER buffer
+                        assert flags[r][s] >= k
+                        assert buf[s][w] == at_signal[s][k], "the reader does not see the owner's positions of this pass"
+            elif op == "read_end":
+                for s in range(G):
+                    if s != r:
+                        assert buf[s][w] == at_signal[s][k], "the buffer changed under the reader"
+                    reading[r][s] = None
+                wrote[r] = False
