@@ -667,7 +667,7 @@ int mrsb_destroy(mrsb_handle h) {
                   h->ds.cmd,    h->ds.ff,     h->ds.flags,    h->ds.mode,     h->ds.gpos,         h->d_params,      h->d_pset,    h->d_stage,
                   h->d_idx,     h->grid.bucket, h->grid.rank, h->grid.count, h->grid.aabb, h->grid.begin, h->grid.rec, h->grid.pairs,
                   h->grid.counters, h->grid.tl, h->grid.scan_state, h->grid.halo_rec, h->grid.halo_bucket, h->grid.halo_rank, h->grid.halo_n, h->grid.halo_work,
-                  h->grid.nl_count, h->grid.nl_items, h->grid.nl_active, h->grid.ctl};
+                  h->grid.nl_count, h->grid.nl_items, h->grid.nl_active, h->grid.act_items, h->grid.ctl};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -878,6 +878,7 @@ int mrsb_create(const mrsb_create_info* info, mrsb_handle* out) {
       CREATE_RC(dalloc(&g.nl_count, size_t(g.nl_ld)));
       CREATE_RC(dalloc(&g.nl_items, size_t(MRSB_NL_CAP) * size_t(g.nl_ld)));
       CREATE_RC(dalloc(&g.nl_active, size_t(g.nl_ld)));
+      CREATE_RC(dalloc(&g.act_items, size_t(MRSB_NL_CAP) * size_t(g.nl_ld)));
     }
     set_collision_geometry(h, g.nl_count != nullptr && s.n_global == s.n);
   }

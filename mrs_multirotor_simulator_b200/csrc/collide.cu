@@ -72,6 +72,9 @@ namespace {
 
 #define DEV __device__ __forceinline__
 
+#define NL_LIVE 0x80000000u     // bit 31 of nl_count[]: the UAV's external force may be non-zero
+#define NL_CROWDED 0x40000000u  // bit 30: more than MRSB_NL_CAP candidates; nl_items[0][uav] = its record in the table
+
 DEV unsigned long long now_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -541,8 +544,6 @@ DEV void process_pair(const DevState& s, const DevGrid& g, int crash_mode, doubl
 }
 
 // SIM:356-358: forces replace external_force_ for the next tick (zero in crash mode, SIM:315-319)
-#define NL_LIVE 0x80000000u     // bit 31 of nl_count[]: the UAV's external force may be non-zero
-#define NL_CROWDED 0x40000000u  // bit 30: more than MRSB_NL_CAP candidates; nl_items[0][uav] = its record in the table
 // li: (external) local index; the force rows and the flags live in the UAV's slot of the tiled arrays (DevState::perm)
 DEV int64_t slot_of(const DevState& s, int64_t li) { return s.perm ? int64_t(s.perm[li]) : li; }
 DEV void store_result(const DevState& s, int64_t li, const PairAcc& acc) {
@@ -732,11 +733,20 @@ __global__ void __launch_bounds__(128) build_lists_kernel(DevState s, DevGrid g)
 
 // The UAVs with something to check on list-only passes, compacted in INDEX order (their accesses to the list columns, positions
 // and forces then coalesce): slot = exclusive count of such UAVs before it (scan_kernel<true> over the count words).
+// The compacted entry holds everything a list-only pass needs to start on: {local index, count word} in `nl_active`, and the
+// UAV's list again, slot-major by ENTRY (`act_items`) — the check then has two dependent memory levels (entry -> positions)
+// instead of four (entry -> count word -> list -> positions).
 __global__ void __launch_bounds__(256) compact_kernel(DevGrid g, const uint32_t* __restrict__ slot, int64_t n) {
   const int64_t li = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (li >= n) return;
-  const bool work = (g.nl_count[li] & 0x7FFFFFFFu) != 0u;
-  if (work) g.nl_active[slot[li]] = int32_t(li);
+  const uint32_t word = g.nl_count[li];
+  const bool     work = (word & 0x7FFFFFFFu) != 0u;
+  if (work) {
+    const uint32_t k   = slot[li];
+    g.nl_active[k]     = make_uint2(uint32_t(li), word);
+    const uint32_t cnt = (word & NL_CROWDED) ? 1u : (word & ~(NL_LIVE | NL_CROWDED));  // crowded: slot 0 holds its record index
+    for (uint32_t c = 0; c < cnt; c++) g.act_items[int64_t(c) * g.nl_ld + k] = g.nl_items[int64_t(c) * g.nl_ld + li];
+  }
   if (li == n - 1) g.ctl->n_active = slot[li] + (work ? 1u : 0u);
 }
 
@@ -795,14 +805,14 @@ DEV void check_crowded(const DevState& s, const DevGrid& g, int crash_mode, doub
 // One UAV that has something to check: the exact predicate on the CURRENT positions of its listed candidates.
 // (Tried and dropped: remembering each candidate's distance at build time and skipping the fetch while
 // d_build - 2 D is still above sqrt(3) — the extra dependent load cost more than the skipped gathers.)
-DEV void check_one(const DevState& s, const DevGrid& g, int crash_mode, double rebounce, int64_t li) {
-  const uint32_t word = g.nl_count[li];
+// k: the UAV's entry in the compacted arrays; first4: the first four slots of its list (fetched with the entry)
+DEV void check_one(const DevState& s, const DevGrid& g, int crash_mode, double rebounce, uint32_t k, int64_t li, uint32_t word, const int32_t* first4) {
   const uint32_t cnt  = word & ~(NL_LIVE | NL_CROWDED);
   // forces were written from outside since the last pass (this pass' index <= write_all_until): replace them all
   const bool     live = (word & NL_LIVE) || g.ctl->n_passes <= g.ctl->write_all_until;
   PairAcc acc;
   if (word & NL_CROWDED) {
-    check_crowded(s, g, crash_mode, rebounce, li + s.shard_begin, uint32_t(g.nl_items[li]), acc);
+    check_crowded(s, g, crash_mode, rebounce, li + s.shard_begin, uint32_t(first4[0]), acc);
   } else if (cnt) {
     const int64_t gi = li + s.shard_begin;
     const double* qp = s.gpos + 3 * gi;
@@ -813,7 +823,7 @@ DEV void check_one(const DevState& s, const DevGrid& g, int crash_mode, double r
       int32_t gj[4];
       double  r[4][3];
 #pragma unroll
-      for (int u = 0; u < 4; u++) gj[u] = base + u < cnt ? g.nl_items[int64_t(base + u) * g.nl_ld + li] : -1;
+      for (int u = 0; u < 4; u++) gj[u] = base + u < cnt ? (base == 0 ? first4[u] : g.act_items[int64_t(base + u) * g.nl_ld + k]) : -1;
 #pragma unroll
       for (int u = 0; u < 4; u++) load_pos(s, int64_t(max(gj[u], 0)), r[u][0], r[u][1], r[u][2]);
 #pragma unroll
@@ -823,7 +833,7 @@ DEV void check_one(const DevState& s, const DevGrid& g, int crash_mode, double r
     if (hits) {
       const Geom Gi      = load_geom(s, gi);
       auto       process = [&](uint32_t c) {
-        const int64_t gj = g.nl_items[int64_t(c) * g.nl_ld + li];
+        const int64_t gj = g.act_items[int64_t(c) * g.nl_ld + k];
         double        rx, ry, rz;
         load_pos(s, gj, rx, ry, rz);
         process_pair(s, g, crash_mode, rebounce, gi, qx, qy, qz, Gi, gj, rx, ry, rz, acc);
@@ -842,7 +852,7 @@ DEV void check_one(const DevState& s, const DevGrid& g, int crash_mode, double r
           uint32_t bc   = 0;
           for (uint32_t m = hits; m; m &= m - 1) {
             const uint32_t c  = uint32_t(__ffs(int(m)) - 1);
-            const int64_t  gj = g.nl_items[int64_t(c) * g.nl_ld + li];
+            const int64_t  gj = g.act_items[int64_t(c) * g.nl_ld + k];
             if (gj > last && gj < best) best = gj, bc = c;
           }
           if (best == INT64_MAX) break;
@@ -856,7 +866,11 @@ DEV void check_one(const DevState& s, const DevGrid& g, int crash_mode, double r
   const bool nz = nonzero(acc);
   if (live || nz) store_result(s, li, acc);
   else if (acc.crashed_me) s.flags[slot_of(s, li)] |= FLAG_CRASHED;
-  if (nz != bool(word & NL_LIVE)) g.nl_count[li] = (word & ~NL_LIVE) | (nz ? NL_LIVE : 0u);
+  if (nz != bool(word & NL_LIVE)) {
+    const uint32_t nw = (word & ~NL_LIVE) | (nz ? NL_LIVE : 0u);
+    g.nl_count[li]    = nw;
+    g.nl_active[k].y  = nw;
+  }
 }
 
 // A list-only pass: the compacted UAVs that have something to check, grid-stride.
@@ -866,7 +880,14 @@ __global__ void __launch_bounds__(256, 4) check_kernel(DevState s, DevGrid g, in
   if (skip_if_rebuild && g.ctl->rebuild) return;
   if (blockIdx.x == 0 && threadIdx.x == 0) stamp(g, 4, now_ns());
   const uint32_t n_active = g.ctl->n_active;
-  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n_active; k += gridDim.x * blockDim.x) check_one(s, g, crash_mode, rebounce, g.nl_active[k]);
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n_active; k += gridDim.x * blockDim.x) {
+    // the entry and the head of its list together: k is all their addresses need
+    const uint2 e = g.nl_active[k];
+    int32_t     first4[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) first4[u] = g.act_items[int64_t(u) * g.nl_ld + k];
+    check_one(s, g, crash_mode, rebounce, k, int64_t(e.x), e.y, first4);
+  }
 }
 
 // First kernel of every pass, one warp.

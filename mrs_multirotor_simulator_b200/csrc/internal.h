@@ -161,7 +161,8 @@ struct DevGrid {
   uint32_t* nl_count;   // [nl_ld] candidates of each local UAV; bit 31: its external force may be non-zero (nullptr: no lists)
   int32_t*  nl_items;   // [MRSB_NL_CAP][nl_ld] their global indices, slot-major
   int64_t   nl_ld;
-  int32_t*  nl_active;  // [n_local] local indices of the UAVs with a candidate (or the crowded mark), ascending
+  uint2*    nl_active;  // [n_local] {local index, count word} of the UAVs with a candidate (or the crowded mark), ascending
+  int32_t*  act_items;  // [MRSB_NL_CAP][nl_ld] their lists again, slot-major by ENTRY of nl_active (what a list-only pass reads)
   NlCtl*    ctl;
   uint32_t* bucket;     // [n_global] bucket of each UAV, 0xFFFFFFFF = not inserted (remote and outside this shard's box)
   uint32_t* rank;       // [n_global] arrival rank inside its bucket

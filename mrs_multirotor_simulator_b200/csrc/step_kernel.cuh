@@ -365,7 +365,8 @@ struct TileIn {
 // per thread after the last read through `in` (the staged kernel re-arms its TMA there).
 template <int NM_T, int MODE_T, bool ONE, class Hook>
 DEV void step_uav(const DevState& s, const TileIn& in, const int64_t tile, const uint32_t flags0, const DevParams* batch_params, const int32_t pset,
-                  const double dt, const double inv_dt, const int k_sub_arg, const int any_moment, uint32_t& disp_bits, Hook after_loads) {
+                  const double dt, const double inv_dt, const int k_sub_arg, const int any_moment, uint32_t& disp_bits, Hook after_loads,
+                  double* park = nullptr) {
   // batch_params: the whole batch's single parameter set in the constant bank (staged kernel), or
   // nullptr -> this UAV's entry of the table in HBM (read-only path)
   const DevParams* __restrict__ P = batch_params ? batch_params : s.params + pset;
@@ -498,7 +499,28 @@ DEV void step_uav(const DevState& s, const TileIn& in, const int64_t tile, const
 
   Vec3 imu = mk(0, 0, 0);
 
+  // K > 1 staged kernels: the PID state (up to 24 doubles) would stay live across the whole substep loop on top of the RK4's live
+  // set — more than 255 registers hold.  It waits in a private column of shared memory between the cascades instead
+  // (`park`: 24 rows of 128 doubles).
+  volatile double* const pk = (!ONE && park) ? park + threadIdx.x : nullptr;
+  // first PID that can be on this kernel's path (12: none, e.g. ActuatorCmd): the others are never touched
+  constexpr int kPidLo = MODE_T < 0 ? 0 : MODE_T == MRSB_POSITION_CMD ? 0 : MODE_T >= MRSB_VELOCITY_HDG_RATE_CMD ? 3 : MODE_T >= MRSB_ATTITUDE_CMD ? 6 : MODE_T >= MRSB_ATTITUDE_RATE_CMD ? 9 : 12;
+  if (!ONE && pk) {
+#pragma unroll
+    for (int k = kPidLo; k < 12; k++) {
+      pk[k * MRSB_TILE]        = pe[k];
+      pk[(12 + k) * MRSB_TILE] = pi[k];
+    }
+  }
+
   for (int sub = 0; sub < k_sub; sub++) {
+    if (!ONE && pk) {
+#pragma unroll
+      for (int k = kPidLo; k < 12; k++) {
+        pe[k] = pk[k * MRSB_TILE];
+        pi[k] = pk[(12 + k) * MRSB_TILE];
+      }
+    }
     // ======================= controller cascade (US:304-374) =================================
     double u[MRSB_NM];
 #pragma unroll
@@ -653,6 +675,13 @@ DEV void step_uav(const DevState& s, const TileIn& in, const int64_t tile, const
     }
 
     const bool last = ONE || (sub == k_sub - 1);
+    if (!ONE && pk && !last) {
+#pragma unroll
+      for (int k = kPidLo; k < 12; k++) {
+        pk[k * MRSB_TILE]        = pe[k];
+        pk[(12 + k) * MRSB_TILE] = pi[k];
+      }
+    }
     if (last) {  // controller state is final for this launch: store it now, not after the RK4 (register pressure)
 #pragma unroll
       for (int k = 0; k < 12; k++) {
@@ -850,7 +879,7 @@ __global__ void __launch_bounds__(MRSB_STEP_THREADS, MRSB_STEP_MINB(ONE, MODE_T)
     uav_step_staged_kernel(DevState s, const __grid_constant__ DevParams params, double dt, double inv_dt, int k_sub, int any_moment, int64_t n_tiles) {
   // `params`: the one parameter set of the whole batch, passed BY VALUE: it lives in the constant
   // bank, so airframe constants and gains are instruction operands instead of ~80 loads per UAV
-  extern __shared__ __align__(128) double sm[];  // SM_ROWS x 128 doubles (tile image)
+  extern __shared__ __align__(128) double sm[];  // SM_ROWS x 128 doubles (tile image) [+ PID_ROWS x 128: PID parking, K > 1]
   __shared__ uint64_t bar;
   if (threadIdx.x == 0) mbar_init(&bar, 1);
   __syncthreads();
@@ -873,10 +902,13 @@ __global__ void __launch_bounds__(MRSB_STEP_THREADS, MRSB_STEP_MINB(ONE, MODE_T)
     if (next < n_tiles) flags_next = s.flags[min(next * MRSB_TILE + threadIdx.x, s.n - 1)];
     mbar_wait(&bar, phase);
     phase ^= 1u;
-    step_uav<NM_T, MODE_T, ONE>(s, in, tile, flags_cur, &params, 0, dt, inv_dt, k_sub, any_moment, disp_bits, [&] {
-      __syncthreads();  // every lane has its inputs in registers: the image may be overwritten
-      if (threadIdx.x == 0 && next < n_tiles) stage_tile<NM_T, MODE_T>(s, params, sm, &bar, next);
-    });
+    step_uav<NM_T, MODE_T, ONE>(
+        s, in, tile, flags_cur, &params, 0, dt, inv_dt, k_sub, any_moment, disp_bits,
+        [&] {
+          __syncthreads();  // every lane has its inputs in registers: the image may be overwritten
+          if (threadIdx.x == 0 && next < n_tiles) stage_tile<NM_T, MODE_T>(s, params, sm, &bar, next);
+        },
+        ONE ? nullptr : sm + SM_ROWS * MRSB_TILE);
     flags_cur = flags_next;
   }
   report_displacement(s, disp_bits);
@@ -912,9 +944,9 @@ void launch_one(const DevState& s, const DevParams* uniform_params, double dt, i
   if constexpr (NM_T > 0 && MODE_T >= 0) if (uniform_params && !getenv("MRSB_NO_STAGING")) {
     // enough tiles to fill the machine more than once: persistent CTAs + TMA staging hide the HBM
     // latency behind the integration of the previous tile
-    const size_t smem = size_t(SM_ROWS) * MRSB_TILE * sizeof(double);
     auto launch = [&](auto one) -> bool {
       constexpr bool kOne = decltype(one)::value;
+      const size_t   smem = size_t(SM_ROWS + (kOne ? 0 : PID_ROWS)) * MRSB_TILE * sizeof(double);  // tile image (+ PID parking rows, K > 1)
       const int      grid = staged_grid<NM_T, MODE_T, kOne>(smem);
       if (grid <= 0 || n_tiles <= grid) return false;
       uav_step_staged_kernel<NM_T, MODE_T, kOne><<<grid, threads, smem, st>>>(s, *uniform_params, dt, inv_dt, k, any_moment, n_tiles);
