@@ -450,7 +450,7 @@ def run_b200(args):
     cmd_host = torch.from_numpy(cmd).pin_memory()
     pos_host = [torch.empty((n_local, 3), dtype=torch.float64).pin_memory() for _ in range(2)]
 
-    def e2e_loop(n_ticks, pipelined, upload_every=1):
+    def e2e_loop(n_ticks, pipelined, upload_every=1, out=None):
         """Every tick: VelocityHdgRate rows H2D (every `upload_every`-th tick), makeStep + handleCollisions (mrsb_run: one graph launch),
         positions D2H — through the C ABI.  pipelined: the upload of tick t+1 and the download of tick t-1 overlap tick t
         (mrsb_*_async); otherwise the blocking setInput/getState pair."""
@@ -465,7 +465,7 @@ def run_b200(args):
                     _lib.check(L.mrsb_set_input_velocity_hdg_rate(batch.h, n_local, None, C.c_void_p(cmd_host.data_ptr())))
             _lib.check(L.mrsb_run(batch.h, DT, 1, 1, 1))
             if pipelined:
-                _lib.check(L.mrsb_get_positions_async(batch.h, C.c_void_p(pos_host[t & 1].data_ptr())))
+                _lib.check(L.mrsb_get_positions_async(batch.h, C.c_void_p((out or pos_host)[t & 1].data_ptr())))
             else:
                 _lib.check(L.mrsb_get_state(batch.h, n_local, None, C.c_void_p(pos_host[0].data_ptr()), None, None, None, None))
         batch.sync()  # uploads, compute and downloads have all landed
@@ -480,6 +480,14 @@ def run_b200(args):
     # the downloaded positions are the simulation's: compare the last snapshot with a blocking read
     assert np.array_equal(last, batch.get_state(fields=("x",))["x"]), "e2e positions differ from a blocking read"
     e2e_10_s = e2e_loop(n_e2e, True, upload_every=10)
+    # ... and a viewer that follows every fourth UAV only (mrsb_set_position_subset): commands on every 10th tick, 6.3 MB of positions per tick
+    every4 = np.arange(0, n_local, 4, dtype=np.int32)
+    batch.set_position_subset(every4)
+    sub_host = [torch.empty((len(every4), 3), dtype=torch.float64).pin_memory() for _ in range(2)]
+    e2e_loop(3, True, upload_every=10, out=sub_host)
+    e2e_sub_s = e2e_loop(n_e2e, True, upload_every=10, out=sub_host)
+    assert np.array_equal(sub_host[(n_e2e - 1) & 1].numpy(), batch.get_state(idx=every4, fields=("x",))["x"]), "subset download differs from a blocking read"
+    batch.set_position_subset(None)
     e2e_loop(3, False)
     e2e_blocking_s = e2e_loop(min(n_e2e, 50), False)
     e2e_value = N_UAVS * n_e2e / e2e_s
@@ -633,11 +641,13 @@ def run_b200(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(cmd_host.numel() * 8), "d2h_bytes_per_step": int(pos_host[0].numel() * 8),
                     "steps": n_e2e, "blocking_api_value": N_UAVS * min(n_e2e, 50) / e2e_blocking_s,
                     "commands_every_10th_tick_value": N_UAVS * n_e2e / e2e_10_s,
+                    "commands_every_10th_tick_positions_of_every_4th_uav_value": N_UAVS * n_e2e / e2e_sub_s,
                     "h2d_gbs_achieved": cmd_host.numel() * 8 * n_e2e / e2e_s / 1e9, "d2h_gbs_achieved": pos_host[0].numel() * 8 * n_e2e / e2e_s / 1e9,
                     "note": "per rank, every tick, via the C ABI: VelocityHdgRate rows H2D from pinned memory (mrsb_set_input_async), one tick (mrsb_run), "
                             "positions D2H to pinned memory (mrsb_get_positions_async); upload of tick t+1 and download of tick t-1 overlap tick t on "
                             "separate streams (the tick is then as long as its PCIe upload: see h2d_gbs_achieved); commands_every_10th_tick_value = commands "
                             "uploaded on every 10th tick only (callback rate below tick rate), positions still downloaded every tick; "
+                            "..._positions_of_every_4th_uav_value = the same with mrsb_set_position_subset(every 4th UAV): 6.3 MB down per tick; "
                             "blocking_api_value = mrsb_set_input + mrsb_get_state"},
             "gpu_launches": int(round(launches)), "roofline": roofline, "cpu_baseline": cpu, "secondary": secondary, "parity": parity}
     print(json.dumps(line), flush=True)

@@ -188,6 +188,9 @@ int mrsb_set_input_device(mrsb_handle h, int32_t mode, int64_t n, const int32_t*
  *    compute; `out_xyz` is valid after mrsb_sync (or mrsb_wait_downloads). */
 int mrsb_set_input_async(mrsb_handle h, int32_t mode, const double* payload, int32_t stride);
 int mrsb_get_positions_async(mrsb_handle h, double* out_xyz);
+/* Which UAVs mrsb_get_positions_async downloads from now on: the n UAVs idx[] (out_xyz then holds [n][3], in idx order) — a viewer
+ * that follows part of the swarm does not pay PCIe for all of it.  idx == NULL or n == 0: all of them again.  Synchronises. */
+int mrsb_set_position_subset(mrsb_handle h, int64_t n, const int32_t* idx);
 int mrsb_wait_uploads(mrsb_handle h);
 int mrsb_wait_downloads(mrsb_handle h);
 

@@ -125,6 +125,11 @@ class UavBatch:
         """Positions [n][3] -> host address `out_ptr` (pinned), downloaded on its own stream; valid after sync()."""
         check(self._L.mrsb_get_positions_async(self.h, out_ptr))
 
+    def set_position_subset(self, idx=None):
+        """The UAVs get_positions_async downloads from now on (None: all)."""
+        idx = _idx(idx)
+        check(self._L.mrsb_set_position_subset(self.h, 0 if idx is None else len(idx), _ptr(idx)))
+
     def set_feedforward(self, kind, payload, idx=None):
         """kind: 'acceleration_hdg_rate' | 'acceleration_hdg' | 'velocity_hdg' | 'velocity_hdg_rate' (uav_system.hpp:254-272)."""
         idx = _idx(idx)

@@ -162,6 +162,8 @@ struct mrsb_sim {
   double*      d_snap[2] = {nullptr, nullptr};  // position snapshots [n_local][3]
   cudaEvent_t  ev_up[2] = {nullptr, nullptr}, ev_applied[2] = {nullptr, nullptr}, ev_snap[2] = {nullptr, nullptr}, ev_down[2] = {nullptr, nullptr};
   uint64_t     n_up = 0, n_down = 0;
+  int32_t*     d_sub_idx = nullptr;  // mrsb_set_position_subset: the UAVs mrsb_get_positions_async downloads (nullptr: all)
+  int64_t      n_sub     = 0;
 
   // the collision pass is a fixed set of launches with fixed arguments: replayed as a CUDA graph (one per
   // gather-buffer parity; with neighbour lists the table rebuild sits in a conditional node of it);
@@ -649,6 +651,7 @@ int mrsb_destroy(mrsb_handle h) {
     for (cudaEvent_t e : {h->ev_up[k], h->ev_applied[k], h->ev_snap[k], h->ev_down[k]})
       if (e) cudaEventDestroy(e);
   }
+  if (h->d_sub_idx) cudaFree(h->d_sub_idx);
   if (h->up_stream) cudaStreamDestroy(h->up_stream);
   if (h->down_stream) cudaStreamDestroy(h->down_stream);
   drop_collision_graphs(h);
@@ -950,17 +953,38 @@ int mrsb_get_positions_async(mrsb_handle h, double* out_xyz) {
   int rc = ensure_pipeline(h);
   if (rc) return rc;
   const int    k     = int(h->n_down & 1);
-  const size_t bytes = sizeof(double) * 3 * size_t(h->ds.n);
+  const size_t bytes = sizeof(double) * 3 * size_t(h->d_sub_idx ? h->n_sub : h->ds.n);
   if (h->n_down >= 2) CU(cudaStreamWaitEvent(h->stream, h->ev_down[k], 0));  // the snapshot buffer was downloaded two reads ago
   if (!(h->ds.opts & STEP_OPT_GPOS)) return fail(MRSB_ERR_STATE, "packed positions are switched off (mrsb_set_outputs)");
   // pull exchange: the buffer being written holds the latest positions only once something wrote it since the last pass
   const double* latest = (h->p2p && !h->wrote_since_pass) ? h->gbuf[h->pass_no & 1] : h->ds.gpos;
-  CU(cudaMemcpyAsync(h->d_snap[k], latest + 3 * h->ds.shard_begin, bytes, cudaMemcpyDeviceToDevice, h->stream));
+  if (h->d_sub_idx) {
+    h->n_launches += launch_gather_xyz(latest + 3 * h->ds.shard_begin, h->n_sub, h->d_sub_idx, h->d_snap[k], h->stream);
+  } else {
+    CU(cudaMemcpyAsync(h->d_snap[k], latest + 3 * h->ds.shard_begin, bytes, cudaMemcpyDeviceToDevice, h->stream));
+  }
   CU(cudaEventRecord(h->ev_snap[k], h->stream));
   CU(cudaStreamWaitEvent(h->down_stream, h->ev_snap[k], 0));
   CU(cudaMemcpyAsync(out_xyz, h->d_snap[k], bytes, cudaMemcpyDeviceToHost, h->down_stream));
   CU(cudaEventRecord(h->ev_down[k], h->down_stream));
   h->n_down++;
+  return MRSB_OK;
+}
+
+int mrsb_set_position_subset(mrsb_handle h, int64_t n, const int32_t* idx) {
+  GUARD(h);
+  if (h->down_stream) CU(cudaStreamSynchronize(h->down_stream));
+  CU(cudaStreamSynchronize(h->stream));
+  if (h->d_sub_idx) CU(cudaFree(h->d_sub_idx));
+  h->d_sub_idx = nullptr;
+  h->n_sub     = 0;
+  if (!idx || n <= 0) return MRSB_OK;  // back to "all of them"
+  for (int64_t k = 0; k < n; k++)
+    if (idx[k] < 0 || idx[k] >= h->ds.n) return fail(MRSB_ERR_INVALID, "idx[%lld]=%d outside 0..%lld", (long long)k, idx[k], (long long)h->ds.n - 1);
+  if (n > h->ds.n) return fail(MRSB_ERR_INVALID, "a subset of more than n_local UAVs");
+  CU(cudaMalloc(&h->d_sub_idx, sizeof(int32_t) * size_t(n)));
+  CU(cudaMemcpy(h->d_sub_idx, idx, sizeof(int32_t) * size_t(n), cudaMemcpyHostToDevice));
+  h->n_sub = n;
   return MRSB_OK;
 }
 

@@ -220,6 +220,7 @@ int launch_gather_vprev(const DevState& s, int64_t n, const int32_t* idx_dev, do
 // zero the state (last error and integral) of PIDs [pid0, pid0 + n_pids)
 int launch_reset_pid(const DevState& s, int64_t n, const int32_t* idx_dev, int pid0, int n_pids, cudaStream_t stream);
 int launch_timeout_input(const DevState& s, int64_t n, const int32_t* idx_dev, cudaStream_t stream);
+int launch_gather_xyz(const double* xyz_dev, int64_t n, const int32_t* idx_dev, double* out_dev, cudaStream_t stream);
 int launch_tracker_cmd(const DevState& s, int64_t n, const int32_t* idx_dev, const double* rows_dev, cudaStream_t stream);
 int launch_observe(const DevState& s, int what, int64_t n, const int32_t* idx_dev, double* out_dev, int stride, cudaStream_t stream);
 int launch_set_pset(int32_t* pset_dev, int64_t n, const int32_t* idx_dev, int64_t offset, const int32_t* values_dev, cudaStream_t stream);

@@ -171,6 +171,14 @@ __global__ void tracker_cmd_kernel(DevState s, int64_t n, const int32_t* __restr
   s.flags[i] |= FLAG_FF_VEL_HDG | FLAG_FF_VEL_HDG_RATE | FLAG_FF_ACC_HDG | FLAG_FF_ACC_HDG_RATE;
 }
 
+// packed positions of a subset: out[k] = xyz[idx[k]] (both packed [.][3])
+__global__ void gather_xyz_kernel(const double* __restrict__ xyz, int64_t n, const int32_t* __restrict__ idx, double* __restrict__ out) {
+  const int64_t k = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const double* p = xyz + 3 * int64_t(idx[k]);
+  out[3 * k] = p[0], out[3 * k + 1] = p[1], out[3 * k + 2] = p[2];
+}
+
 // collision geometry of the addressed UAVs from their parameter set
 __global__ void set_geom_kernel(double* __restrict__ geom, int64_t n, const int32_t* __restrict__ idx, int64_t offset, const int32_t* __restrict__ pset,
                                 const DevParams* __restrict__ params) {
@@ -363,6 +371,11 @@ int launch_gather_vprev(const DevState& s, int64_t n, const int32_t* idx, double
 int launch_reset_pid(const DevState& s, int64_t n, const int32_t* idx, int pid0, int n_pids, cudaStream_t st) {
   if (n <= 0) return 0;
   reset_pid_kernel<<<nblk(n), 256, 0, st>>>(s, n, idx, pid0, n_pids);
+  return 1;
+}
+int launch_gather_xyz(const double* xyz, int64_t n, const int32_t* idx, double* out, cudaStream_t st) {
+  if (n <= 0) return 0;
+  gather_xyz_kernel<<<nblk(n), 256, 0, st>>>(xyz, n, idx, out);
   return 1;
 }
 int launch_tracker_cmd(const DevState& s, int64_t n, const int32_t* idx, const double* rows, cudaStream_t st) {

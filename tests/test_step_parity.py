@@ -331,3 +331,33 @@ def test_pipelined_host_io_equals_blocking_io():
     fa, fb = a.get_full_state(), b.get_full_state()
     for k in fa:
         assert np.array_equal(fa[k], fb[k]), k
+
+
+def test_position_subset_download():
+    """mrsb_set_position_subset: mrsb_get_positions_async then delivers the positions of the chosen UAVs only, in the chosen order
+    (mixed airframes: the batch is bucketed internally, the subset is in the caller's indices); None switches back to all."""
+    import torch
+
+    from mrs_multirotor_simulator_b200 import UavBatch
+
+    n = 3000
+    tou = (np.arange(n) % 2).astype(np.int32)
+    b = UavBatch([af("x500"), af("f550")], type_of_uav=tou, spawn_xyz=grid_spawn(n, z=5.0), n=n)
+    b.set_input(O.VELOCITY_HDG_RATE_CMD, np.stack([rand(1, 1, n, -2, 2), rand(1, 2, n, -2, 2), rand(1, 3, n, -1, 1), rand(1, 4, n, -1, 1)], axis=1))
+    sub = np.array([2999, 0, 17, 1500, 18, 1, 2998], dtype=np.int32)
+    b.set_position_subset(sub)
+    outs = [torch.zeros((len(sub), 3), dtype=torch.float64).pin_memory() for _ in range(6)]
+    ref = []
+    for t in range(6):
+        b.make_step(0.01)
+        b.get_positions_async(outs[t].data_ptr())
+        ref.append(b.get_state(idx=sub, fields=("x",))["x"].copy())
+    b.sync()
+    for t in range(6):
+        assert np.array_equal(outs[t].numpy(), ref[t]), t
+    b.set_position_subset(None)
+    full = torch.zeros((n, 3), dtype=torch.float64).pin_memory()
+    b.make_step(0.01)
+    b.get_positions_async(full.data_ptr())
+    b.sync()
+    assert np.array_equal(full.numpy(), b.get_state(fields=("x",))["x"])
