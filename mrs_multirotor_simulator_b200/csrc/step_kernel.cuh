@@ -294,8 +294,11 @@ DEV Vec3 attitude_error(const Rot& Rd, const Rot& R) {
 // kernels gain from 3 CTAs (168 registers, 12 warps per SM) except PositionCmd, whose extra PID
 // state then spills; the K > 1 kernels keep PID state, command and motor speeds live across the
 // substep loop and are faster with 2 CTAs (<= 255 registers, no spills).
+#ifndef MRSB_STEP_MINB_K1
+#define MRSB_STEP_MINB_K1 3
+#endif
 #ifndef MRSB_STEP_MINB
-#define MRSB_STEP_MINB(ONE, MODE_T) (((ONE) && (MODE_T) != MRSB_POSITION_CMD) ? 3 : 2)
+#define MRSB_STEP_MINB(ONE, MODE_T) (((ONE) && (MODE_T) != MRSB_POSITION_CMD) ? MRSB_STEP_MINB_K1 : 2)
 #endif
 
 // ---- TMA / mbarrier plumbing for the staged kernel ---------------------------------------------
@@ -844,34 +847,41 @@ __global__ void __launch_bounds__(MRSB_STEP_THREADS, MRSB_STEP_MINB(ONE, MODE_T)
 
 // ---- staged kernel: persistent CTAs, the NEXT tile's inputs are fetched by the TMA unit into
 // shared memory while the current tile is being integrated out of registers ----------------------
-// shared-memory tile image (rows of 128 doubles): st 18 | rpm 8 | pid 24 | cmd 12 | fext 3
-#define SM_ST 0
-#define SM_RPM (SM_ST + ST_ROWS)
-#define SM_PID (SM_RPM + MRSB_NM)
-#define SM_CMD (SM_PID + PID_ROWS)
-#define SM_FEXT (SM_CMD + CMD_ROWS)
-#define SM_ROWS (SM_FEXT + F3_ROWS)
+// shared-memory tile image (rows of 128 doubles): st 18 | rpm n | pid rows on the mode's path | command rows of the mode | fext 3
+// Image layout of one instantiation: only the rows the mode touches take space (44-50 KiB for the velocity modes of a quad
+// instead of 65), so that more CTAs fit per SM.  PID rows keep their spacing (last error of PID k in image row k - pid_lo of the
+// PID block, integral in row 12 + k - pid_lo: one pointer serves both), which leaves pid_lo unused rows between the two groups.
+template <int NM_T, int MODE_T>
+struct Img {
+  static constexpr int  pid_lo   = MODE_T == MRSB_POSITION_CMD ? 0 : MODE_T >= MRSB_VELOCITY_HDG_RATE_CMD ? 3 : MODE_T >= MRSB_ATTITUDE_CMD ? 6 : MODE_T >= MRSB_ATTITUDE_RATE_CMD ? 9 : 12;
+  static constexpr int  cmd_rows = MODE_T == MRSB_ACTUATOR_CMD ? NM_T : MODE_T == MRSB_ATTITUDE_CMD ? 10 : MODE_T == MRSB_TILT_HDG_RATE_CMD ? 5 : 4;
+  static constexpr bool hdg      = MODE_T == MRSB_POSITION_CMD || MODE_T == MRSB_VELOCITY_HDG_CMD || MODE_T == MRSB_ACCELERATION_HDG_CMD;
+  static constexpr int  ST       = 0;
+  static constexpr int  RPM      = ST + ST_ROWS;
+  static constexpr int  PID      = RPM + NM_T;                         // image row of PID row `pid_lo`
+  static constexpr int  CMD      = PID + (pid_lo < 12 ? PID_ROWS - pid_lo : 0);
+  static constexpr int  FEXT     = CMD + (hdg ? CMD_ROWS : cmd_rows);  // the cached cos / sin sit in command rows 10, 11
+  static constexpr int  ROWS     = FEXT + F3_ROWS;
+};
 
 template <int NM_T, int MODE_T>
 DEV void stage_tile(const DevState& s, const DevParams& P, double* sm, uint64_t* bar, int64_t tile) {
-  const bool rate_int = P.rate_ki[0] != 0.0 || P.rate_ki[1] != 0.0 || P.rate_ki[2] != 0.0;  // same test as step_uav
   static_assert(MODE_T >= 0 && NM_T > 0, "the staged kernel is for batches with a uniform input mode and motor count");
+  using I = Img<NM_T, MODE_T>;
+  const bool     rate_int = P.rate_ki[0] != 0.0 || P.rate_ki[1] != 0.0 || P.rate_ki[2] != 0.0;  // same test as step_uav
   constexpr int  kRow     = MRSB_TILE * int(sizeof(double));
-  // first PID on the mode's path (PIDs 0-2 position, 3-5 velocity, 6-8 attitude, 9-11 rate; 12 = none)
-  constexpr int  pid_lo   = MODE_T == MRSB_POSITION_CMD ? 0 : MODE_T >= MRSB_VELOCITY_HDG_RATE_CMD ? 3 : MODE_T >= MRSB_ATTITUDE_CMD ? 6 : MODE_T >= MRSB_ATTITUDE_RATE_CMD ? 9 : 12;
-  constexpr int  cmd_rows = MODE_T == MRSB_ACTUATOR_CMD ? NM_T : MODE_T == MRSB_ATTITUDE_CMD ? 10 : MODE_T == MRSB_TILT_HDG_RATE_CMD ? 5 : 4;
-  constexpr bool hdg      = MODE_T == MRSB_POSITION_CMD || MODE_T == MRSB_VELOCITY_HDG_CMD || MODE_T == MRSB_ACCELERATION_HDG_CMD;
+  constexpr int  pid_lo   = I::pid_lo;
   // integrals: rows 12 + pid_lo .. 23, without the three dead rate integrals when their ki is zero
   const int      int_rows = pid_lo < 12 ? (rate_int ? 12 - pid_lo : 9 - pid_lo) : 0;
-  const uint32_t bytes    = uint32_t(kRow) * uint32_t(ST_ROWS + NM_T + (12 - pid_lo) + int_rows + cmd_rows + (hdg ? 2 : 0) + F3_ROWS);
+  const uint32_t bytes    = uint32_t(kRow) * uint32_t(ST_ROWS + NM_T + (12 - pid_lo) + int_rows + I::cmd_rows + (I::hdg ? 2 : 0) + F3_ROWS);
   mbar_expect_tx(bar, bytes);
-  tma_load(sm + SM_ST * MRSB_TILE, s.st + (tile * ST_ROWS) * MRSB_TILE, kRow * ST_ROWS, bar);
-  tma_load(sm + SM_RPM * MRSB_TILE, s.rpm + (tile * MRSB_NM) * MRSB_TILE, kRow * NM_T, bar);
-  if (pid_lo < 12) tma_load(sm + (SM_PID + pid_lo) * MRSB_TILE, s.pid + (tile * PID_ROWS + pid_lo) * MRSB_TILE, kRow * (12 - pid_lo), bar);
-  if (int_rows > 0) tma_load(sm + (SM_PID + 12 + pid_lo) * MRSB_TILE, s.pid + (tile * PID_ROWS + 12 + pid_lo) * MRSB_TILE, uint32_t(kRow) * uint32_t(int_rows), bar);
-  tma_load(sm + SM_CMD * MRSB_TILE, s.cmd + (tile * CMD_ROWS) * MRSB_TILE, kRow * cmd_rows, bar);
-  if (hdg) tma_load(sm + (SM_CMD + CMD_COS) * MRSB_TILE, s.cmd + (tile * CMD_ROWS + CMD_COS) * MRSB_TILE, kRow * 2, bar);
-  tma_load(sm + SM_FEXT * MRSB_TILE, s.fext + (tile * F3_ROWS) * MRSB_TILE, kRow * F3_ROWS, bar);
+  tma_load(sm + I::ST * MRSB_TILE, s.st + (tile * ST_ROWS) * MRSB_TILE, kRow * ST_ROWS, bar);
+  tma_load(sm + I::RPM * MRSB_TILE, s.rpm + (tile * MRSB_NM) * MRSB_TILE, kRow * NM_T, bar);
+  if (pid_lo < 12) tma_load(sm + I::PID * MRSB_TILE, s.pid + (tile * PID_ROWS + pid_lo) * MRSB_TILE, kRow * (12 - pid_lo), bar);
+  if (int_rows > 0) tma_load(sm + (I::PID + 12) * MRSB_TILE, s.pid + (tile * PID_ROWS + 12 + pid_lo) * MRSB_TILE, uint32_t(kRow) * uint32_t(int_rows), bar);
+  tma_load(sm + I::CMD * MRSB_TILE, s.cmd + (tile * CMD_ROWS) * MRSB_TILE, kRow * I::cmd_rows, bar);
+  if (I::hdg) tma_load(sm + (I::CMD + CMD_COS) * MRSB_TILE, s.cmd + (tile * CMD_ROWS + CMD_COS) * MRSB_TILE, kRow * 2, bar);
+  tma_load(sm + I::FEXT * MRSB_TILE, s.fext + (tile * F3_ROWS) * MRSB_TILE, kRow * F3_ROWS, bar);
 }
 
 template <int NM_T, int MODE_T, bool ONE>
@@ -879,18 +889,19 @@ __global__ void __launch_bounds__(MRSB_STEP_THREADS, MRSB_STEP_MINB(ONE, MODE_T)
     uav_step_staged_kernel(DevState s, const __grid_constant__ DevParams params, double dt, double inv_dt, int k_sub, int any_moment, int64_t n_tiles) {
   // `params`: the one parameter set of the whole batch, passed BY VALUE: it lives in the constant
   // bank, so airframe constants and gains are instruction operands instead of ~80 loads per UAV
-  extern __shared__ __align__(128) double sm[];  // SM_ROWS x 128 doubles (tile image) [+ PID_ROWS x 128: PID parking, K > 1]
+  using I = Img<NM_T, MODE_T>;
+  extern __shared__ __align__(128) double sm[];  // I::ROWS x 128 doubles (tile image) [+ PID_ROWS x 128: PID parking, K > 1]
   __shared__ uint64_t bar;
   if (threadIdx.x == 0) mbar_init(&bar, 1);
   __syncthreads();
   int64_t tile = blockIdx.x;
   if (threadIdx.x == 0 && tile < n_tiles) stage_tile<NM_T, MODE_T>(s, params, sm, &bar, tile);
   TileIn in;
-  in.st   = sm + SM_ST * MRSB_TILE + threadIdx.x;
-  in.rpm  = sm + SM_RPM * MRSB_TILE + threadIdx.x;
-  in.pid  = sm + SM_PID * MRSB_TILE + threadIdx.x;
-  in.cmd  = sm + SM_CMD * MRSB_TILE + threadIdx.x;
-  in.fext = sm + SM_FEXT * MRSB_TILE + threadIdx.x;
+  in.st   = sm + I::ST * MRSB_TILE + threadIdx.x;
+  in.rpm  = sm + I::RPM * MRSB_TILE + threadIdx.x;
+  in.pid  = sm + (I::PID - I::pid_lo) * MRSB_TILE + threadIdx.x;  // addressed by PID row number; rows below pid_lo are never read
+  in.cmd  = sm + I::CMD * MRSB_TILE + threadIdx.x;
+  in.fext = sm + I::FEXT * MRSB_TILE + threadIdx.x;
   uint32_t phase = 0;
   // the per-UAV word that is not part of the tile image is prefetched one tile ahead
   int64_t  i0        = min(tile * MRSB_TILE + threadIdx.x, s.n - 1);
@@ -908,7 +919,7 @@ __global__ void __launch_bounds__(MRSB_STEP_THREADS, MRSB_STEP_MINB(ONE, MODE_T)
           __syncthreads();  // every lane has its inputs in registers: the image may be overwritten
           if (threadIdx.x == 0 && next < n_tiles) stage_tile<NM_T, MODE_T>(s, params, sm, &bar, next);
         },
-        ONE ? nullptr : sm + SM_ROWS * MRSB_TILE);
+        ONE ? nullptr : sm + I::ROWS * MRSB_TILE);
     flags_cur = flags_next;
   }
   report_displacement(s, disp_bits);
@@ -946,7 +957,7 @@ void launch_one(const DevState& s, const DevParams* uniform_params, double dt, i
     // latency behind the integration of the previous tile
     auto launch = [&](auto one) -> bool {
       constexpr bool kOne = decltype(one)::value;
-      const size_t   smem = size_t(SM_ROWS + (kOne ? 0 : PID_ROWS)) * MRSB_TILE * sizeof(double);  // tile image (+ PID parking rows, K > 1)
+      const size_t   smem = size_t(Img<NM_T, MODE_T>::ROWS + (kOne ? 0 : PID_ROWS)) * MRSB_TILE * sizeof(double);  // tile image (+ PID parking rows, K > 1)
       const int      grid = staged_grid<NM_T, MODE_T, kOne>(smem);
       if (grid <= 0 || n_tiles <= grid) return false;
       uav_step_staged_kernel<NM_T, MODE_T, kOne><<<grid, threads, smem, st>>>(s, *uniform_params, dt, inv_dt, k, any_moment, n_tiles);
