@@ -87,6 +87,16 @@ def checksum(a):
     return int(np.ascontiguousarray(a, dtype=np.float64).view(np.uint64).sum(dtype=np.uint64))
 
 
+def combine_checksums(cs, dist, device=None):
+    """The swarm's checksum from the shards': the wrapping sum over ranks (a uint64 travels as two int64 words)."""
+    import torch
+
+    t = torch.tensor([cs & 0x7FFFFFFFFFFFFFFF, cs >> 63], dtype=torch.int64, device=device)
+    parts = [torch.zeros_like(t) for _ in range(dist.get_world_size())]
+    dist.all_gather(parts, t)
+    return sum(int(p[0].item()) | (int(p[1].item()) << 63) for p in parts) & 0xFFFFFFFFFFFFFFFF
+
+
 class ClockSampler:
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -420,10 +430,7 @@ def run_b200(args):
     x_now = batch.get_state(fields=("x",))["x"]
     cs = checksum(x_now)
     if dist is not None:
-        t = torch.tensor([cs & 0x7FFFFFFFFFFFFFFF, cs >> 63], dtype=torch.int64, device=dev)
-        parts = [torch.zeros_like(t) for _ in range(world)]
-        dist.all_gather(parts, t)
-        cs = sum(int(p[0].item()) | (int(p[1].item()) << 63) for p in parts) & 0xFFFFFFFFFFFFFFFF
+        cs = combine_checksums(cs, dist, dev)
 
     # shards that fit into L2: the same blocks again without the flush between ticks (what a running simulation sees: tick t + 1
     # reads what tick t wrote), reported beside the headline

@@ -9,6 +9,12 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
 from mrs_multirotor_simulator_b200.sharding import connect, gather_layout, shard_range
 
 
@@ -37,6 +43,12 @@ def _worker(rank, world, port, n, q):
     parts = [torch.empty(c, dtype=torch.float64) for _, c in lay]
     dist.all_gather(parts, mine)
     buf = torch.cat(parts).numpy().reshape(n, 3)
+    # bench.py's state checksum: the shards' checksums combine (wrapping sum over ranks) to the checksum of the whole swarm
+    import bench
+
+    whole = np.stack([4.0 * (np.arange(n) % 32), 4.0 * (np.arange(n) // 32), 0.5 * np.arange(n)], axis=1) - 1e9 / 7.0  # negative values: top bits set
+    combined = bench.combine_checksums(bench.checksum(whole[begin:begin + count]), dist)
+    assert combined == bench.checksum(whole), (combined, bench.checksum(whole))
     q.put((rank, b.joined[0], b.joined[1], b.joined[2] == bytes(range(128)), float(np.abs(buf[:, 2] - 0.5 * np.arange(n)).max())))
     dist.destroy_process_group()
 
