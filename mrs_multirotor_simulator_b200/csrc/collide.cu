@@ -876,7 +876,11 @@ DEV void check_one(const DevState& s, const DevGrid& g, int crash_mode, double r
 // A list-only pass: the compacted UAVs that have something to check, grid-stride.
 // skip_if_rebuild: this launch runs BESIDE the conditional rebuild node of the graph, not behind it; on a rebuilding pass it does
 // nothing — the rebuild's body ends with its own launch of this kernel.
-__global__ void __launch_bounds__(256, 4) check_kernel(DevState s, DevGrid g, int crash_mode, double rebounce, int skip_if_rebuild) {
+#ifndef MRSB_CHECK_THREADS
+#define MRSB_CHECK_THREADS 256
+#define MRSB_CHECK_MINB 4
+#endif
+__global__ void __launch_bounds__(MRSB_CHECK_THREADS, MRSB_CHECK_MINB) check_kernel(DevState s, DevGrid g, int crash_mode, double rebounce, int skip_if_rebuild) {
   if (skip_if_rebuild && g.ctl->rebuild) return;
   if (blockIdx.x == 0 && threadIdx.x == 0) stamp(g, 4, now_ns());
   const uint32_t n_active = g.ctl->n_active;
@@ -1059,6 +1063,7 @@ int launch_collide_check(const DevState& s, const DevGrid& g, const PeerView& pv
     refresh_halo_kernel<<<unsigned(std::max<int64_t>(1, std::min<int64_t>((g.halo_cap + 63) / 64, 148 * 2))), 64, 0, stream>>>(s, g, pv);
     own += 1;
   }
-  check_kernel<<<unsigned(std::min<int64_t>((s.n + 255) / 256, 148 * 4)), 256, 0, stream>>>(s, g, crash_mode, rebounce, beside_rebuild);
+  check_kernel<<<unsigned(std::min<int64_t>((s.n + MRSB_CHECK_THREADS - 1) / MRSB_CHECK_THREADS, 148 * MRSB_CHECK_MINB)), MRSB_CHECK_THREADS, 0, stream>>>(s, g, crash_mode, rebounce,
+                                                                                                                                                       beside_rebuild);
   return own + 1;
 }
