@@ -139,6 +139,14 @@ void mrsb_controller_params_default(mrsb_controller_params* out);
  * pseudo-inverse of the allocation matrix, row-major [n_motors][4] in out[MRSB_MAX_MOTORS*4]. */
 void mrsb_mixer_allocation_of(const mrsb_model_params* params, double* out);
 
+/* How mrsb_create lays out a batch (pure host computation, no device needed).  A batch with 2..8 airframe types present is stored
+ * bucketed: its UAVs sorted stably by type, every type padded to whole tiles of 128 slots, so that each tile of the device
+ * arrays holds one airframe.  type_of_local_uav[n]: type of every local UAV.  Outputs (any may be NULL except n_slots):
+ * slot_of_uav[n], *n_slots (a multiple of 128), bucket_first_slot[n_types] (-1: type absent or batch not bucketed) and
+ * bucket_count[n_types].  Returns the number of buckets (1 = not bucketed: slot_of_uav[i] = i) or a negative mrsb_status. */
+int mrsb_bucket_layout(int64_t n, int32_t n_types, const int32_t* type_of_local_uav, int32_t* slot_of_uav, int64_t* n_slots, int64_t* bucket_first_slot,
+                       int64_t* bucket_count);
+
 /* ---- lifetime: UavSystem(params, spawn_pos, spawn_heading) for every UAV (US:144-153) ----- */
 int mrsb_create(const mrsb_create_info* info, mrsb_handle* out);
 int mrsb_destroy(mrsb_handle h);

@@ -53,6 +53,7 @@ SIGNATURES = {
     "mrsb_model_params_finalize": (None, [C.POINTER(ModelParams)]),
     "mrsb_controller_params_default": (None, [C.POINTER(ControllerParams)]),
     "mrsb_mixer_allocation_of": (None, [C.POINTER(ModelParams), C.c_void_p]),
+    "mrsb_bucket_layout": (C.c_int, [C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.c_void_p, C.c_void_p]),
     "mrsb_create": (C.c_int, [C.POINTER(CreateInfo), C.POINTER(H)]),
     "mrsb_destroy": (C.c_int, [H]),
     "mrsb_sync": (C.c_int, [H]),

@@ -678,6 +678,42 @@ int mrsb_destroy(mrsb_handle h) {
   return MRSB_OK;
 }
 
+int mrsb_bucket_layout(int64_t n, int32_t n_types, const int32_t* type_of_local_uav, int32_t* slot_of_uav, int64_t* n_slots, int64_t* bucket_first_slot,
+                       int64_t* bucket_count) {
+  if (n < 0 || n_types < 1 || (n > 0 && !type_of_local_uav) || !n_slots) return fail(MRSB_ERR_INVALID, "bad argument");
+  std::vector<int64_t> per_type(size_t(n_types), 0);
+  for (int64_t i = 0; i < n; i++) {
+    const int t = type_of_local_uav[i];
+    if (t < 0 || t >= n_types) return fail(MRSB_ERR_INVALID, "type_of_uav of local UAV %lld is %d, outside 0..%d", (long long)i, t, n_types - 1);
+    per_type[size_t(t)]++;
+  }
+  int present = 0;
+  for (int64_t c : per_type) present += c > 0;
+  for (int t = 0; t < n_types; t++) {
+    if (bucket_first_slot) bucket_first_slot[t] = -1;
+    if (bucket_count) bucket_count[t] = per_type[size_t(t)];
+  }
+  if (present < 2 || present > 8 || getenv("MRSB_NO_BUCKETS")) {
+    // one airframe (or too many to launch one kernel each): slots in the caller's order
+    *n_slots = std::max<int64_t>(MRSB_TILE, round_up(n, MRSB_TILE));
+    for (int64_t i = 0; i < n && slot_of_uav; i++) slot_of_uav[i] = int32_t(i);
+    for (int t = 0; t < n_types && bucket_first_slot; t++)
+      if (per_type[size_t(t)] && present == 1) bucket_first_slot[t] = 0;
+    return 1;
+  }
+  std::vector<int64_t> next(size_t(n_types), 0);
+  int64_t              slot = 0;
+  for (int t = 0; t < n_types; t++) {
+    if (!per_type[size_t(t)]) continue;
+    next[size_t(t)] = slot;
+    if (bucket_first_slot) bucket_first_slot[t] = slot;
+    slot += round_up(per_type[size_t(t)], MRSB_TILE);
+  }
+  *n_slots = slot;
+  for (int64_t i = 0; i < n && slot_of_uav; i++) slot_of_uav[i] = int32_t(next[size_t(type_of_local_uav[i])]++);
+  return present;
+}
+
 int mrsb_create(const mrsb_create_info* info, mrsb_handle* out) {
   if (!info || !out) return fail(MRSB_ERR_INVALID, "null argument");
   *out = nullptr;
@@ -724,45 +760,33 @@ int mrsb_create(const mrsb_create_info* info, mrsb_handle* out) {
   s.n_global    = info->n_global;
   s.shard_begin = info->shard_begin;
   s.n_groups32  = (s.n + 31) / 32;
-  // Buckets: the local UAVs sorted (stably) by airframe type, every type padded to whole 128-UAV tiles, when the batch has
-  // between 2 and 8 types (more: one bucket, generic kernel).  MRSB_NO_BUCKETS=1 keeps the external order.
+  // Buckets: the local UAVs sorted (stably) by airframe type, every type padded to whole 128-UAV tiles (mrsb_bucket_layout)
   {
-    std::vector<int64_t> per_type(size_t(info->n_types), 0);
-    for (int64_t i = 0; i < s.n; i++) {
-      const int t = info->type_of_uav ? info->type_of_uav[s.shard_begin + i] : 0;
-      if (t < 0 || t >= info->n_types) {
-        mrsb_destroy(h);
-        return fail(MRSB_ERR_INVALID, "type_of_uav[%lld]=%d outside 0..%d", (long long)(s.shard_begin + i), t, info->n_types - 1);
-      }
-      per_type[size_t(t)]++;
+    std::vector<int32_t> type_local(size_t(std::max<int64_t>(s.n, 1)), 0);
+    for (int64_t i = 0; i < s.n; i++) type_local[size_t(i)] = info->type_of_uav ? info->type_of_uav[s.shard_begin + i] : 0;
+    std::vector<int64_t> first(size_t(info->n_types), -1), count(size_t(info->n_types), 0);
+    std::vector<int32_t> slot_of(size_t(std::max<int64_t>(s.n, 1)), 0);
+    int64_t              n_slots   = 0;
+    const int            n_buckets = mrsb_bucket_layout(s.n, info->n_types, type_local.data(), slot_of.data(), &n_slots, first.data(), count.data());
+    if (n_buckets < 0) {
+      mrsb_destroy(h);
+      return n_buckets;
     }
-    int present = 0;
-    for (int64_t c : per_type) present += c > 0;
-    if (present >= 2 && present <= 8 && !getenv("MRSB_NO_BUCKETS")) {
-      std::vector<int64_t> next(size_t(info->n_types), 0);
-      int64_t              slot = 0;
+    s.ld = n_slots;
+    if (n_buckets > 1) {
       for (int t = 0; t < info->n_types; t++) {
-        if (!per_type[size_t(t)]) continue;
+        if (first[size_t(t)] < 0) continue;
         mrsb_sim::Bucket b;
-        b.slot0 = slot, b.count = per_type[size_t(t)];
+        b.slot0 = first[size_t(t)], b.count = count[size_t(t)];
         h->buckets.push_back(b);
-        next[size_t(t)] = slot;
-        slot += round_up(b.count, MRSB_TILE);
       }
-      s.ld = slot;
-      h->perm_host.assign(size_t(s.n), 0);
+      h->perm_host.assign(slot_of.begin(), slot_of.begin() + s.n);
       h->inv_host.assign(size_t(s.ld), -1);
-      for (int64_t i = 0; i < s.n; i++) {
-        const int t                     = info->type_of_uav[s.shard_begin + i];
-        const int64_t sl                = next[size_t(t)]++;
-        h->perm_host[size_t(i)]         = int32_t(sl);
-        h->inv_host[size_t(sl)]         = int32_t(i);
-      }
+      for (int64_t i = 0; i < s.n; i++) h->inv_host[size_t(slot_of[size_t(i)])] = int32_t(i);
     } else {
       mrsb_sim::Bucket b;
       b.slot0 = 0, b.count = s.n;
       h->buckets.push_back(b);
-      s.ld = std::max<int64_t>(128, round_up(info->n_local, 128));
     }
   }
   const size_t ld = size_t(s.ld);

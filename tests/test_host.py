@@ -187,3 +187,40 @@ def test_pull_exchange_buffer_protocol_on_a_scheduler_model():
                         assert buf[s][w] == at_signal[s][k], "the buffer changed under the reader"
                     reading[r][s] = None
                 wrote[r] = False
+
+
+def test_bucket_layout_of_mixed_batches():
+    """mrsb_bucket_layout (what mrsb_create uses): a batch with 2..8 airframe types is stored sorted stably by type, every type
+    padded to whole 128-slot tiles — each tile of the device arrays then holds ONE airframe; callers keep their own indices."""
+    L = _lib.lib()
+    rng = np.random.default_rng(3)
+    for n, n_types in ((1, 1), (300, 1), (64, 2), (3000, 3), (5000, 8), (777, 9), (129, 2), (3 * 58001, 3)):
+        tou = (np.arange(n) * 7 % n_types).astype(np.int32) if n_types <= 3 else rng.integers(0, n_types, n).astype(np.int32)
+        slot = np.full(n, -1, dtype=np.int32)
+        first = np.zeros(n_types, dtype=np.int64)
+        count = np.zeros(n_types, dtype=np.int64)
+        n_slots = C.c_int64(0)
+        nb = L.mrsb_bucket_layout(n, n_types, tou.ctypes.data_as(C.c_void_p), slot.ctypes.data_as(C.c_void_p), C.byref(n_slots),
+                                  first.ctypes.data_as(C.c_void_p), count.ctypes.data_as(C.c_void_p))
+        present = len(np.unique(tou))
+        assert n_slots.value % 128 == 0 and n_slots.value >= n
+        assert np.array_equal(count, np.bincount(tou, minlength=n_types))
+        if present < 2 or present > 8:
+            assert nb == 1 and np.array_equal(slot, np.arange(n))  # one airframe, or too many for a launch each: the caller's order
+            continue
+        assert nb == present
+        assert len(np.unique(slot)) == n and slot.min() >= 0 and slot.max() < n_slots.value  # a permutation into the slots
+        type_of_slot = np.full(n_slots.value, -1)
+        type_of_slot[slot] = tou
+        tiles = type_of_slot.reshape(-1, 128)
+        for row in tiles:  # every tile: one airframe (plus padding at the end of a bucket)
+            assert len(set(row[row >= 0])) <= 1
+        for t in range(n_types):
+            mine = np.flatnonzero(tou == t)
+            if len(mine) == 0:
+                assert first[t] == -1
+                continue
+            assert first[t] % 128 == 0
+            assert np.array_equal(slot[mine], first[t] + np.arange(len(mine)))  # stable: the caller's order inside a bucket
+    bad = np.array([0, 5], dtype=np.int32)
+    assert L.mrsb_bucket_layout(2, 2, bad.ctypes.data_as(C.c_void_p), None, C.byref(C.c_int64(0)), None, None) == -1
