@@ -23,6 +23,9 @@
 //     multiplication by such a reciprocal (<= 2 ulp instead of correctly rounded);
 //   * the NaN -> 0 scrub of the slopes (MM:361-365) and the NaN -> restore check (MM:228-233) first
 //     screen the exponent fields with integer max (any Inf/NaN?) and only then do the exact test;
+//   * exp(-dt/tau) of the motor lag (MM:244) comes from the parameter table (evaluated once per set and dt by
+//     prep_params_kernel), 1/dt from the host; the integral of a rate PID whose ki is zero (the default) is dead state
+//     and is neither loaded nor stored; the K > 1 staged kernels park the PID state in shared memory between substeps;
 //   * every fused multiply-add is written out (`fma`) and the file is compiled with -fmad=false, so
 //     that all instantiations of the kernel (direct / staged, K = 1 / K > 1, any register budget)
 //     produce the same bits: K fused substeps equal K launches, a sharded swarm equals the unsharded one.
